@@ -1,0 +1,131 @@
+/*
+ * pqh_knn.h -- C ABI of libpqh_knn.so, the B200 (sm_100a) implementation of the
+ * exact k-nearest-neighbour hot path of trukanduk/pq_huffman.
+ *
+ * Every entry point takes plain pointers and sizes; no CUDA, torch or C++ types
+ * cross this boundary.  File:line citations are relative to the reference's
+ * src/ directory.
+ *
+ * Drop-in symbol
+ * --------------
+ * knn_full_thread() below has exactly the prototype of Yael v438's
+ * <yael/nn.h> knn_full_thread, the single unresolved symbol of the reference's
+ * compute_nn_fast (call site compute_nn_fast.c:478-481, link line
+ * Makefile:5,28-30).  Linking the reference's unmodified objects against
+ * libpqh_knn.so instead of -lyael moves the search onto the GPU; see
+ * INTEGRATION.md.
+ *
+ * Error behaviour follows the reference's convention for this path
+ * (compute_nn_fast.c:154-156, fast_nn_block_loader2.c:88-91): the void entry
+ * points print a message to stderr and exit(1) on an unrecoverable error (no
+ * usable CUDA device, CUDA/NCCL failure, out of device memory).  There is NO
+ * CPU fallback.  The pqh_* entry points that return int report 0 on success
+ * and a negative PQH_E* code otherwise, and pqh_last_error() returns the text.
+ */
+#ifndef PQH_KNN_H_
+#define PQH_KNN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQH_OK 0
+#define PQH_EINVAL (-1)  /* bad argument */
+#define PQH_ENODEV (-2)  /* no usable sm_100 CUDA device */
+#define PQH_ECUDA (-3)   /* CUDA runtime / driver failure */
+#define PQH_ENOMEM (-4)  /* host or device allocation failed */
+#define PQH_ECOMM (-5)   /* multi-GPU exchange failed */
+
+/*
+ * Replaces: Yael knn_full_thread, called at compute_nn_fast.c:478-481 (dead
+ * twin at :416-419) and, through ynumpy.knn, at compute_nn.py:22.
+ *
+ *   distance_type  must be 2 (squared L2), the only value the reference passes
+ *   nq, nb, d      number of queries, base vectors, dimensions
+ *   k              neighbours per query (the reference passes min(num_nn,n-1)+1)
+ *   b              base,    float32[nb x d] row-major, host memory
+ *   v              queries, float32[nq x d] row-major, host memory; v == b
+ *                  (same pointer, nq == nb) selects the self-join the reference
+ *                  uses: query i is base row i
+ *   b_weights      must be NULL (the reference passes NULL)
+ *   assign         out, int32[nq x k]: base positions, ascending distance
+ *   dis            out, float32[nq x k]: squared L2, bit-identical to the scalar
+ *                  FP32 definition get_real_dist (compute_nn_fast.c:304-311)
+ *   n_thread       accepted for compatibility; the GPU path ignores it
+ *
+ * Order within a row: ascending (distance, base position).  For a self-join,
+ * column 0 is the query itself with distance 0 (the caller drops column 0 as
+ * "self", compute_nn_fast.c:498, compute_nn.py:23-24).  If k > nb the unfilled
+ * tail of a row is assign = -1, dis = +inf.
+ *
+ * Buffers are caller-owned; nothing is retained after return.
+ */
+void knn_full_thread(int distance_type, int nq, int nb, int d, int k, const float *b,
+                     const float *v, const float *b_weights, int *assign, float *dis,
+                     int n_thread);
+
+/*
+ * Context control.  The first search creates the context lazily on the devices
+ * named by $PQH_DEVICES (comma separated ordinals, default: device 0 only);
+ * these calls make it explicit.  Replaces nothing in the reference (it has no
+ * device state); they exist so that compute_nn_fast's hundreds of per-block
+ * calls (run(), compute_nn_fast.c:556-610) reuse streams, pinned staging and
+ * device buffers instead of re-creating them.
+ */
+int pqh_knn_init(const int *devices, int n_devices); /* NULL/0: $PQH_DEVICES or {0} */
+void pqh_knn_shutdown(void);
+int pqh_knn_device_count(void);                      /* devices in the live context, 0 if none */
+const char *pqh_last_error(void);
+
+/*
+ * Search algorithm selection (debug / test hook; the default is AUTO).
+ *   PQH_ALGO_AUTO    tensor-core pass + exact re-rank + certificate, rows that
+ *                    fail the certificate are redone by the exact kernel
+ *   PQH_ALGO_EXACT   FP32 SIMT kernel only (no tensor cores)
+ */
+#define PQH_ALGO_AUTO 0
+#define PQH_ALGO_EXACT 1
+int pqh_knn_set_algo(int algo);
+
+/*
+ * Row-sliced search: queries [q_begin, q_end) of v against all nb rows of b.
+ * Row q of the result is written at assign + (q - q_begin) * k (and likewise
+ * dis).  This is the unit of work one rank of a multi-process run owns
+ * (partition by query-block rows); knn_full_thread is
+ * pqh_knn_search_rows over [0, nq).  self_join != 0 means query q is base row
+ * q (what v == b means for knn_full_thread).
+ */
+int pqh_knn_search_rows(int nq_total, int nb, int d, int k, const float *b, const float *v,
+                        int self_join, int q_begin, int q_end, int *assign, float *dis);
+
+/*
+ * Device-resident variant for callers that already hold the vectors in HBM
+ * (bench.py's device-timed arm, a future GPU loader): all pointers are device
+ * pointers on `device`, the call is asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = the context's own stream, synchronous).  d_work must
+ * point to pqh_knn_workspace_bytes(...) bytes of device scratch.
+ */
+long long pqh_knn_workspace_bytes(int nq, int nb, int d, int k);
+int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const float *d_b,
+                          const float *d_v, int self_join, int q_begin, int q_end,
+                          int *d_assign, float *d_dis, void *d_work, long long work_bytes,
+                          void *stream);
+
+/*
+ * Counters of the last search on this thread's context, for tests and
+ * bench.py: how the rows were resolved and how many kernels were launched.
+ */
+typedef struct pqh_knn_stats {
+    long long rows;            /* query rows searched */
+    long long rows_tensor;     /* rows resolved by the tensor-core pass + certificate */
+    long long rows_exact;      /* rows (re)done by the exact FP32 kernel */
+    long long launches;        /* kernels launched */
+    double ms_total;           /* wall time of the call, host clock */
+    double ms_h2d, ms_kernels, ms_d2h; /* device-event times of the phases */
+} pqh_knn_stats_t;
+int pqh_knn_last_stats(pqh_knn_stats_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQH_KNN_H_ */

@@ -1,0 +1,17 @@
+// kernels.h -- host-callable launchers of the kNN kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace pqh {
+
+// ---- knn_exact.cu ----------------------------------------------------------
+size_t exact_smem_bytes();
+int exact_pick_nsplit(int n_rows, int nb, int num_sms);
+size_t exact_workspace_bytes(int n_rows, int kcap, int nsplit);
+cudaError_t launch_knn_exact(const float *d_base, const float *d_queries, const int *d_row_ids,
+                             int q_begin, int out_q_begin, int n_rows, int nb, int d, int k,
+                             int self_join, int *d_assign, float *d_dis, void *d_work,
+                             size_t work_bytes, int num_sms, cudaStream_t stream, int *launches);
+
+}  // namespace pqh

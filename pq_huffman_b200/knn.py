@@ -1,0 +1,109 @@
+"""Host-side mirror of the reference's kNN call for tests and bench.py.
+
+``knn_full_thread`` here has the argument meaning of Yael's function as the
+reference calls it (compute_nn_fast.c:478-481) and of ``ynumpy.knn`` in
+compute_nn.py:22: arrays in, (ids, distances) out, squared L2, ascending, k per
+row.  All arithmetic happens inside libpqh_knn.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+ALGO_AUTO = 0
+ALGO_EXACT = 1
+
+
+class PqhError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise PqhError(f"libpqh_knn error {rc}: {_lib.load().pqh_last_error().decode()}")
+
+
+def init(devices=None):
+    """Create the device context (pqh_knn_init)."""
+    lib = _lib.load()
+    if devices is None:
+        _check(lib.pqh_knn_init(None, 0))
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib.pqh_knn_init(arr, len(devices)))
+
+
+def shutdown():
+    _lib.load().pqh_knn_shutdown()
+
+
+def set_algo(algo):
+    _check(_lib.load().pqh_knn_set_algo(int(algo)))
+
+
+def last_stats():
+    st = _lib.Stats()
+    _check(_lib.load().pqh_knn_last_stats(C.byref(st)))
+    return {name: getattr(st, name) for name, _ in _lib.Stats._fields_}
+
+
+def _as_f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D array [n x d]")
+    return a
+
+
+def knn_full_thread(base, queries=None, k=1, n_thread=1):
+    """Exact squared-L2 kNN through the drop-in symbol.
+
+    ``queries is None`` (or the same array object as ``base``) is the self-join
+    compute_nn_fast performs: row i's first neighbour is i itself.
+    Returns (assign int32[nq,k], dis float32[nq,k]).
+    """
+    lib = _lib.load()
+    b = _as_f32(base)
+    v = b if queries is None or queries is base else _as_f32(queries)
+    if v.shape[1] != b.shape[1]:
+        raise ValueError("dimension mismatch")
+    nq, d = v.shape
+    nb = b.shape[0]
+    assign = np.empty((nq, k), dtype=np.int32)
+    dis = np.empty((nq, k), dtype=np.float32)
+    lib.knn_full_thread(2, nq, nb, d, k, b.ctypes.data, v.ctypes.data, None,
+                        assign.ctypes.data, dis.ctypes.data, n_thread)
+    return assign, dis
+
+
+def search_rows(base, queries, k, q_begin, q_end, self_join=None, out=None):
+    """Rows [q_begin,q_end) of the search (pqh_knn_search_rows): one rank's share."""
+    lib = _lib.load()
+    b = _as_f32(base)
+    v = b if queries is None or queries is base else _as_f32(queries)
+    if self_join is None:
+        self_join = v is b
+    nq, d = v.shape
+    n = q_end - q_begin
+    if out is None:
+        assign = np.empty((n, k), dtype=np.int32)
+        dis = np.empty((n, k), dtype=np.float32)
+    else:
+        assign, dis = out
+    _check(lib.pqh_knn_search_rows(nq, b.shape[0], d, k, b.ctypes.data, v.ctypes.data,
+                                   int(bool(self_join)), q_begin, q_end,
+                                   assign.ctypes.data, dis.ctypes.data))
+    return assign, dis
+
+
+def search_device(device, nq_total, nb, d, k, d_base, d_queries, self_join, q_begin, q_end,
+                  d_assign, d_dis, d_work, work_bytes, stream=None):
+    """Device-pointer search (pqh_knn_search_device); pointers are integers."""
+    lib = _lib.load()
+    _check(lib.pqh_knn_search_device(device, nq_total, nb, d, k, d_base, d_queries,
+                                     int(bool(self_join)), q_begin, q_end, d_assign, d_dis,
+                                     d_work, work_bytes, stream))
+
+
+def workspace_bytes(nq, nb, d, k):
+    return int(_lib.load().pqh_knn_workspace_bytes(nq, nb, d, k))

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the library loads and exports what
+include/pqh_knn.h declares; without a GPU it fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from pq_huffman_b200 import _lib, knn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "pqh_knn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(knn_full_thread|pqh_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_loader_agree():
+    assert declared_functions() == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in declared_functions():
+        assert getattr(lib, name) is not None
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(declared_functions()) <= exported
+    # nothing but the C ABI is exported as a C symbol from our namespace
+    assert not [s for s in exported if s.startswith("pqh_") and s not in _lib.EXPORTS]
+
+
+def test_library_contains_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly_without_fallback():
+    x = np.zeros((8, 4), dtype=np.float32)
+    with pytest.raises(knn.PqhError) as ei:
+        knn.search_rows(x, None, 2, 0, 8)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+    # the void drop-in symbol follows the reference's convention: message + exit(1)
+    code = ("import numpy as np; from pq_huffman_b200 import knn; "
+            "x=np.zeros((8,4),dtype=np.float32); knn.knn_full_thread(x,None,2)")
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert p.returncode == 1
+    assert "libpqh_knn" in p.stderr
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = _lib.load()
+    x = np.zeros((8, 4), dtype=np.float32)
+    out_i = np.zeros((8, 2), dtype=np.int32)
+    out_d = np.zeros((8, 2), dtype=np.float32)
+    rc = lib.pqh_knn_search_rows(8, 8, 4, 2, x.ctypes.data, x.ctypes.data, 1, 5, 3,
+                                 out_i.ctypes.data, out_d.ctypes.data)
+    assert rc == -1 and b"row range" in lib.pqh_last_error()
+    rc = lib.pqh_knn_search_rows(8, 8, 0, 2, x.ctypes.data, x.ctypes.data, 1, 0, 8,
+                                 out_i.ctypes.data, out_d.ctypes.data)
+    assert rc == -1
+    assert lib.pqh_knn_set_algo(77) == -1
+    assert lib.pqh_knn_workspace_bytes(1000, 1000, 16, 9) > 0

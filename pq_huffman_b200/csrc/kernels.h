@@ -9,9 +9,20 @@ namespace pqh {
 size_t exact_smem_bytes();
 int exact_pick_nsplit(int n_rows, int nb, int num_sms);
 size_t exact_workspace_bytes(int n_rows, int kcap, int nsplit);
+size_t exact_workspace_bound(int n_rows_max, int kcap, int num_sms);
 cudaError_t launch_knn_exact(const float *d_base, const float *d_queries, const int *d_row_ids,
-                             int q_begin, int out_q_begin, int n_rows, int nb, int d, int k,
+                             int q_begin, int q_row0, int out_q_begin, int n_rows, int nb, int d,
+                             int k,
                              int self_join, int *d_assign, float *d_dis, void *d_work,
                              size_t work_bytes, int num_sms, cudaStream_t stream, int *launches);
+
+// ---- knn_tc.cu -------------------------------------------------------------
+bool tc_supported(int n_rows, int nb, int d, int k, int self_join);
+size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms);
+cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row0, int q_begin,
+                          int out_q_begin, int n_rows, int nb, int d, int k, int self_join,
+                          int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
+                          int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
+                          unsigned *h_fb_count);
 
 }  // namespace pqh

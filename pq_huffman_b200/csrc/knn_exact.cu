@@ -42,7 +42,8 @@ struct ExactSmem {
 
 __global__ void __launch_bounds__(256)
 knn_exact_kernel(const float *__restrict__ base, const float *__restrict__ queries,
-                 const int *__restrict__ row_ids, int q_begin, int n_rows, int nb, int d, int kcap,
+                 const int *__restrict__ row_ids, int q_begin, int q_row0, int n_rows, int nb,
+                 int d, int kcap,
                  int self_join, int nsplit, int split_rows, key64_t *__restrict__ lists,
                  int *__restrict__ meta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,7 +85,7 @@ knn_exact_kernel(const float *__restrict__ base, const float *__restrict__ queri
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 int col = k0 + lcol + c;
-                qv[c] = (lq >= 0 && col < d) ? queries[(size_t)lq * d + col] : 0.0f;
+                qv[c] = (lq >= 0 && col < d) ? queries[(size_t)(lq - q_row0) * d + col] : 0.0f;
                 bv[c] = (lb < b_hi && col < d) ? base[(size_t)lb * d + col] : 0.0f;
             }
             __syncthreads();  // previous chunk fully consumed
@@ -235,10 +236,22 @@ size_t exact_workspace_bytes(int n_rows, int kcap, int nsplit) {
     return lists + ((meta + 255) & ~(size_t)255) + scratch + 512;
 }
 
+// Upper bound of exact_workspace_bytes over every row count <= n_rows_max (the split
+// count grows as the row count shrinks: tiles * nsplit <= 2 * num_sms + tiles).
+size_t exact_workspace_bound(int n_rows_max, int kcap, int num_sms) {
+    size_t tiles = (size_t)(n_rows_max + TQ - 1) / TQ;
+    size_t slot_splits = (size_t)TQ * (2 * (size_t)num_sms + tiles + 1);
+    size_t slots = tiles * TQ;
+    return slot_splits * (2 * (size_t)kcap * sizeof(key64_t) + sizeof(int)) +
+           slots * 2 * (size_t)kcap * sizeof(key64_t) + 4096;
+}
+
 // Launches the exact search for n_rows query rows (row_ids == nullptr: rows
-// q_begin .. q_begin+n_rows).  Output row for query q is (q - out_q_begin).
+// q_begin .. q_begin+n_rows; otherwise the absolute query ids listed).  Query q's
+// vector is row (q - q_row0) of d_queries; its output row is (q - out_q_begin).
 cudaError_t launch_knn_exact(const float *d_base, const float *d_queries, const int *d_row_ids,
-                             int q_begin, int out_q_begin, int n_rows, int nb, int d, int k,
+                             int q_begin, int q_row0, int out_q_begin, int n_rows, int nb, int d,
+                             int k,
                              int self_join, int *d_assign, float *d_dis, void *d_work,
                              size_t work_bytes, int num_sms, cudaStream_t stream, int *launches) {
     if (n_rows <= 0) return cudaSuccess;
@@ -267,7 +280,7 @@ cudaError_t launch_knn_exact(const float *d_base, const float *d_queries, const 
         if (e != cudaSuccess) return e;
         dim3 grid(tiles, nsplit);
         knn_exact_kernel<<<grid, 256, sizeof(ExactSmem), stream>>>(
-            d_base, d_queries, d_row_ids, q_begin, n_rows, nb, d, kcap, self_join, nsplit,
+            d_base, d_queries, d_row_ids, q_begin, q_row0, n_rows, nb, d, kcap, self_join, nsplit,
             split_rows, lists, meta);
         if (launches) ++*launches;
     } else {

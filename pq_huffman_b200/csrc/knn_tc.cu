@@ -1,0 +1,872 @@
+// knn_tc.cu -- tensor-core kNN: tcgen05/TMEM GEMM with a fused per-row candidate
+// filter, followed by an exact FP32 re-rank with a completeness certificate.
+//
+// Score.  For query x and base y the squared L2 distance is |x|^2 - 2 S with
+// S = x.y - |y|^2/2, so "k smallest distances" == "k largest S" per row.  The
+// kernel computes S' = sigma^2 * S on the tensor cores from FP16 operands:
+//   * prep: x' = fp16(sigma * x) with sigma a power of two putting max|x| in
+//     [2^7, 2^8) (exact for integer-valued data such as SIFT-shaped uint8), and
+//     |y'|^2/2 split into three FP16 pieces q1,q2,q3 with |y'|^2/2 =
+//     4096 q1 + 2 q2 + 2^-10 q3 (+ <2^-30 relative);
+//   * the GEMM K dimension is [x'(d16) | fold(16)]: the A (query) side holds the
+//     constants (4096, 2, 2^-10, 0..), the B (base) side (-q1,-q2,-q3, 0..), so
+//     the accumulator IS S' and the epilogue is a bare threshold compare.
+// Nothing of the nq x nb score matrix reaches HBM: epilogue warps read the
+// accumulator from TMEM (tcgen05.ld), take the max of 32 columns per row and
+// only touch memory for the rare elements above the row's running threshold.
+//
+// Exactness.  Candidates (a superset of the top-L by S') are re-ranked by
+// knn_rerank_kernel with the scalar FP32 sequence of get_real_dist
+// (compute_nn_fast.c:304-311), giving distances bit-identical to the oracle.
+// A row is accepted only if a proven bound shows no non-candidate can beat its
+// k-th exact distance (see certificate in knn_rerank_kernel); other rows are
+// redone by the exact kernel (knn_exact.cu).  So the result is always the
+// oracle's, and the tensor cores only decide how fast it is found.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace pqh {
+
+namespace {
+
+constexpr int TC_ROWS = 256;    // query rows per CTA: two M=128 accumulator tiles
+constexpr int TC_BN = 128;      // base rows per tile (UMMA N)
+constexpr int TC_NSTAGE = 3;    // B-tile ring
+constexpr int TC_MAXSEG = 6;
+constexpr int TC_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_EPI_WARPS = 8;
+constexpr int FOLD_COLS = 16;
+
+struct TcSeg {
+    int k_off;   // element offset in the fp16 operand row (data segments)
+    int bytes;   // row bytes of this K segment: 128 / 64 / 32 (= swizzle span)
+    int fold;    // 1: the |y|^2 fold segment (separate tensors)
+    int a_off;   // byte offset inside the A region
+    int b_off;   // byte offset inside one B stage
+};
+
+struct TcPlan {
+    int nseg;
+    int a_bytes;  // A region bytes (256 rows)
+    int b_bytes;  // one B stage (128 rows)
+    TcSeg seg[TC_MAXSEG];
+};
+
+struct TcArgs {
+    int n_rows;      // query rows in this launch
+    int q_begin;     // absolute query index of row 0 (self-join: also its base position)
+    int q_op_begin;  // row of row 0 inside the A operand tensor
+    int nb;
+    int self_join;
+    int n_qtiles, nsplit, tiles_per_split, n_btiles;
+    int L;
+    key64_t *cand;
+    int *cand_cnt;
+    float *cand_tau;
+    TcPlan plan;
+};
+
+struct TcMaps {
+    CUtensorMap a[3];  // data operand, box 256 rows: SW128 / SW64 / SW32
+    CUtensorMap b[3];  // data operand, box 128 rows
+    CUtensorMap fa;    // fold constants [256 x 16]
+    CUtensorMap fb;    // fold pieces    [nb x 16]
+};
+
+__device__ __forceinline__ int seg_class(int bytes) { return bytes == 128 ? 0 : (bytes == 64 ? 1 : 2); }
+__device__ __forceinline__ uint32_t seg_layout(int bytes) {
+    return bytes == 128 ? 2u : (bytes == 64 ? 4u : 6u);
+}
+
+// power-of-two scale putting maxabs in [2^7, 2^8)
+__host__ __device__ __forceinline__ float scale_from_maxabs_bits(uint32_t bits) {
+    int e = (int)((bits >> 23) & 0xff) - 127;  // maxabs in [2^e, 2^(e+1))
+    if ((bits & 0x7fffffffu) == 0 || e < -100) return 1.0f;
+    int se = 7 - e;
+    if (se > 100) se = 100;
+    if (se < -100) se = -100;
+    uint32_t sb = (uint32_t)(se + 127) << 23;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(sb);
+#else
+    union { uint32_t u; float f; } c; c.u = sb; return c.f;
+#endif
+}
+
+// ------------------------------------------------------------------------------------
+// prep 1: max |x| over a matrix (grid-stride, float4), atomicMax on the IEEE bits
+__global__ void __launch_bounds__(256) maxabs_kernel(const float *__restrict__ x, size_t n,
+                                                     uint32_t *__restrict__ out_bits) {
+    float m = 0.0f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)x) & 15) == 0) {
+        const size_t n4 = n / 4;
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        for (size_t j = i; j < n4; j += stride) {
+            float4 v = __ldg(x4 + j);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        for (size_t j = n4 * 4 + i; j < n; j += stride) m = fmaxf(m, fabsf(x[j]));
+    } else {
+        for (size_t j = i; j < n; j += stride) m = fmaxf(m, fabsf(x[j]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// prep 2: one warp per row: fp16 operand row, exact-ish FP64 squared norm, fold pieces
+struct PrepScalars {
+    uint32_t maxabs_bits;  // max |x| over base and queries
+    uint32_t ymax_bits;    // max scaled base norm |y'| (float bits, rounded up)
+    uint32_t inexact;      // some fp16(sigma*x) != sigma*x
+    uint32_t fb_count;     // rows that failed the certificate
+    uint32_t pad[4];
+};
+
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const float *__restrict__ x, int n, int d, int d16, __half *__restrict__ xh,
+                 double *__restrict__ norm64, __half *__restrict__ fold, int write_fold,
+                 PrepScalars *__restrict__ sc) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float sigma = scale_from_maxabs_bits(sc->maxabs_bits);
+    const float *xr = x + (size_t)row * d;
+    __half *hr = xh + (size_t)row * d16;
+    double acc = 0.0;
+    bool inexact = false;
+    for (int i = lane; i < d16; i += 32) {
+        float v = i < d ? xr[i] : 0.0f;
+        float s = v * sigma;  // exact: power-of-two scale
+        __half h = __float2half_rn(s);
+        if (__half2float(h) != s) inexact = true;
+        hr[i] = h;
+        acc += (double)v * (double)v;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (__any_sync(0xffffffffu, inexact) && lane == 0) atomicOr(&sc->inexact, 1u);
+    if (lane == 0 && norm64) norm64[row] = acc;
+    if (write_fold) {
+        // n' = sigma^2 |y|^2 / 2 = 4096 q1 + 2 q2 + 2^-10 q3 (+ residual)
+        const double np = acc * (double)sigma * (double)sigma * 0.5;
+        __half q1 = __double2half(np / 4096.0);
+        double r1 = np - 4096.0 * (double)__half2float(q1);
+        __half q2 = __double2half(r1 * 0.5);
+        double r2 = r1 - 2.0 * (double)__half2float(q2);
+        __half q3 = __double2half(r2 * 1024.0);
+        if (lane < FOLD_COLS) {
+            __half v = __float2half_rn(0.0f);
+            if (lane == 0) v = __hneg(q1);
+            if (lane == 1) v = __hneg(q2);
+            if (lane == 2) v = __hneg(q3);
+            fold[(size_t)row * FOLD_COLS + lane] = v;
+        }
+        if (lane == 0) {
+            // scaled norm, rounded up so that it is a valid upper bound
+            float yn = __double2float_ru(sqrt(acc) * (double)sigma * (1.0 + 1e-7));
+            atomicMax(&sc->ymax_bits, __float_as_uint(yn));
+        }
+    }
+}
+
+__global__ void fold_const_kernel(__half *__restrict__ fa) {
+    // [256 x 16]: every query row multiplies the base pieces by (4096, 2, 2^-10)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TC_ROWS * FOLD_COLS) return;
+    const int c = i % FOLD_COLS;
+    float v = c == 0 ? 4096.0f : (c == 1 ? 2.0f : (c == 2 ? 0.0009765625f : 0.0f));
+    fa[i] = __float2half_rn(v);
+}
+
+// ------------------------------------------------------------------------------------
+// main kernel
+template <int GCAP>
+struct TcSmemTail {
+    key64_t scratch[TC_EPI_WARPS][GCAP];
+    uint64_t a_full, a_empty;
+    uint64_t b_full[TC_NSTAGE], b_empty[TC_NSTAGE];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int GCAP>
+__device__ __forceinline__ void compact_row(key64_t *sc, key64_t *list, int n, int L, int lane) {
+    for (int i = lane; i < n; i += 32) sc[i] = __ldcg(list + i);
+    warp_sort_keys<GCAP>(sc, n, lane);
+    for (int i = lane; i < L; i += 32) __stcg(list + i, sc[i]);
+    __syncwarp();
+}
+
+template <int GCAP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const TcPlan &plan = args.plan;
+    uint8_t *smA = smem;
+    uint8_t *smB = smA + plan.a_bytes;
+    TcSmemTail<GCAP> &tail =
+        *reinterpret_cast<TcSmemTail<GCAP> *>(smB + TC_NSTAGE * plan.b_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 3; ++i) {
+            ptx::prefetch_tmap(&maps.a[i]);
+            ptx::prefetch_tmap(&maps.b[i]);
+        }
+        ptx::prefetch_tmap(&maps.fa);
+        ptx::prefetch_tmap(&maps.fb);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(&tail.a_full, 1);
+        ptx::mbar_init(&tail.a_empty, 1);
+        for (int i = 0; i < TC_NSTAGE; ++i) {
+            ptx::mbar_init(&tail.b_full[i], 1);
+            ptx::mbar_init(&tail.b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tail.acc_full[i], 1);
+            ptx::mbar_init(&tail.acc_empty[i], TC_EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<512>(&tail.tmem_base);
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = tail.tmem_base;
+
+    const int n_items = args.n_qtiles * args.nsplit;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t ph = 0, a_ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int qt = item / args.nsplit, sp = item % args.nsplit;
+                int t_lo = sp * args.tiles_per_split;
+                int t_hi = t_lo + args.tiles_per_split;
+                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
+                ptx::mbar_arrive_expect_tx(&tail.a_full, plan.a_bytes);
+                for (int s = 0; s < plan.nseg; ++s) {
+                    const TcSeg &sg = plan.seg[s];
+                    if (sg.fold)
+                        ptx::tma_load_2d(smA + sg.a_off, &maps.fa, &tail.a_full, 0, 0);
+                    else
+                        ptx::tma_load_2d(smA + sg.a_off, &maps.a[seg_class(sg.bytes)],
+                                         &tail.a_full, sg.k_off, args.q_op_begin + qt * TC_ROWS);
+                }
+                a_ph ^= 1;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    ptx::mbar_wait(&tail.b_empty[stage], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&tail.b_full[stage], plan.b_bytes);
+                    uint8_t *dst = smB + stage * plan.b_bytes;
+                    for (int s = 0; s < plan.nseg; ++s) {
+                        const TcSeg &sg = plan.seg[s];
+                        if (sg.fold)
+                            ptx::tma_load_2d(dst + sg.b_off, &maps.fb, &tail.b_full[stage], 0,
+                                             t * TC_BN);
+                        else
+                            ptx::tma_load_2d(dst + sg.b_off, &maps.b[seg_class(sg.bytes)],
+                                             &tail.b_full[stage], sg.k_off, t * TC_BN);
+                    }
+                    if (++stage == TC_NSTAGE) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(128, TC_BN);
+            int stage = 0, as = 0;
+            uint32_t ph = 0, acc_ph = 0, a_ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int sp = item % args.nsplit;
+                int t_lo = sp * args.tiles_per_split;
+                int t_hi = t_lo + args.tiles_per_split;
+                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                ptx::mbar_wait(&tail.a_full, a_ph);
+                a_ph ^= 1;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    ptx::mbar_wait(&tail.b_full[stage], ph);
+                    ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
+                    const uint32_t a_base = ptx::smem_u32(smA);
+#pragma unroll 1
+                    for (int g = 0; g < 2; ++g) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + g * 128);
+                        uint32_t acc = 0;
+                        for (int s = 0; s < plan.nseg; ++s) {
+                            const TcSeg &sg = plan.seg[s];
+                            const uint32_t a_addr = a_base + sg.a_off + g * 128 * sg.bytes;
+                            const uint32_t b_addr = b_base + sg.b_off;
+                            const uint32_t sbo = 8 * sg.bytes, lay = seg_layout(sg.bytes);
+                            for (int kk = 0; kk < sg.bytes / 32; ++kk) {
+                                ptx::umma_f16(d_tmem, ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
+                                              ptx::make_smem_desc(b_addr + kk * 32, sbo, lay), idesc,
+                                              acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    ptx::umma_commit(&tail.b_empty[stage]);
+                    ptx::umma_commit(&tail.acc_full[as]);
+                    if (++stage == TC_NSTAGE) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                    as ^= 1;
+                    if (as == 0) acc_ph ^= 1;
+                }
+                ptx::umma_commit(&tail.a_empty);
+            }
+        }
+    } else {
+        // ===================== epilogue: threshold filter =====================
+        const int e = warp - 2;
+        const int g = e >> 2;
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int row_in_cta = g * 128 + quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        key64_t *sc = tail.scratch[e];
+        int as = 0;
+        uint32_t acc_ph = 0;
+        const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int qt = item / args.nsplit, sp = item % args.nsplit;
+            int t_lo = sp * args.tiles_per_split;
+            int t_hi = t_lo + args.tiles_per_split;
+            if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+            const int r = qt * TC_ROWS + row_in_cta;
+            const bool valid = r < args.n_rows;
+            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
+            key64_t *list = args.cand + slot * GCAP;
+            float tau = valid ? NEG_INF : POS_INF;
+            int cnt = 0;
+            long long b_hi = (long long)t_hi * TC_BN;
+            if (b_hi > args.nb) b_hi = args.nb;
+            const int ib_hi = (int)b_hi;
+
+            for (int t = t_lo; t < t_hi; ++t) {
+                ptx::mbar_wait(&tail.acc_full[as], acc_ph);
+                ptx::tc_fence_after_sync();
+                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c) {
+                    uint32_t rr[32];
+                    ptx::tmem_ld_32x32b_x32(tbase + c * 32, rr);
+                    ptx::tmem_wait_ld();
+                    float m = ptx::fmax3(__uint_as_float(rr[0]), __uint_as_float(rr[1]),
+                                         __uint_as_float(rr[2]));
+#pragma unroll
+                    for (int j = 3; j < 31; j += 2)
+                        m = ptx::fmax3(m, __uint_as_float(rr[j]), __uint_as_float(rr[j + 1]));
+                    m = fmaxf(m, __uint_as_float(rr[31]));
+                    const bool hit = m > tau;
+                    if (__any_sync(0xffffffffu, hit)) {
+                        if (hit) {
+                            const int col0 = t * TC_BN + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float v = __uint_as_float(rr[j]);
+                                const int id = col0 + j;
+                                if (v > tau && id < ib_hi && id != self) {
+                                    __stcg(list + cnt, make_key(-v, (uint32_t)id));
+                                    ++cnt;
+                                }
+                            }
+                        }
+                        unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - 32);
+                        while (need) {
+                            const int src = __ffs(need) - 1;
+                            need &= need - 1;
+                            key64_t *l = reinterpret_cast<key64_t *>(
+                                __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+                            const int n = __shfl_sync(0xffffffffu, cnt, src);
+                            compact_row<GCAP>(sc, l, n, args.L, lane);
+                            const key64_t kth = sc[args.L - 1];
+                            __syncwarp();
+                            if (lane == src) {
+                                cnt = args.L;
+                                tau = -key_score(kth);
+                            }
+                        }
+                    }
+                }
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
+                as ^= 1;
+                if (as == 0) acc_ph ^= 1;
+            }
+            if (valid) {
+                args.cand_cnt[slot] = cnt;
+                args.cand_tau[slot] = tau;
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// exact FP32 re-rank + certificate.  One warp per query row.
+constexpr int RR_WARPS = 4;
+
+struct RerankArgs {
+    const float *base;
+    const float *queries;  // row r of this launch is queries[(q_row_begin + r) * d]
+    int q_row_begin;
+    int q_begin;           // absolute query index of row 0 (self-join id, output naming)
+    int out_q_begin;       // output row = q - out_q_begin
+    int n_rows, nb, d, k, kcap, self_join;
+    int nsplit, gcap;
+    const key64_t *cand;
+    const int *cand_cnt;
+    const float *cand_tau;
+    const double *qnorm64;  // |x|^2 of the query rows, indexed like queries (q_row_begin + r)
+    const PrepScalars *sc;
+    int ksteps;             // UMMA K steps per accumulator (for the accumulation bound)
+    int *assign;
+    float *dis;
+    int *fb_rows;           // absolute query ids of rows that failed the certificate
+    uint32_t *fb_count;
+};
+
+template <int NMAX>
+__global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankArgs a) {
+    extern __shared__ __align__(16) unsigned char rr_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    key64_t *keys = reinterpret_cast<key64_t *>(rr_smem) + (size_t)warp * NMAX;
+    float *qrow = reinterpret_cast<float *>(rr_smem + (size_t)RR_WARPS * NMAX * sizeof(key64_t)) +
+                  (size_t)warp * a.d;
+    const int r = blockIdx.x * RR_WARPS + warp;
+    if (r >= a.n_rows) return;
+    const int q = a.q_begin + r;
+
+    // gather the candidate ids of all splits; tau = max over splits
+    int n = 0;
+    float tau = __int_as_float(0xff800000);
+    for (int s = 0; s < a.nsplit; ++s) {
+        const size_t slot = (size_t)r * a.nsplit + s;
+        const int c = a.cand_cnt[slot];
+        const key64_t *l = a.cand + slot * a.gcap;
+        for (int i = lane; i < c; i += 32) keys[n + i] = __ldcg(l + i);
+        n += c;
+        tau = fmaxf(tau, a.cand_tau[slot]);
+    }
+    const float *qsrc = a.queries + (size_t)(a.q_row_begin + r) * a.d;
+    for (int i = lane; i < a.d; i += 32) qrow[i] = qsrc[i];
+    __syncwarp();
+
+    // exact distances: the scalar sequence of get_real_dist, one candidate per lane
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t id = key_pos(keys[i]);
+        const float *brow = a.base + (size_t)id * a.d;
+        float acc = 0.0f;
+        if ((a.d & 3) == 0) {
+            const float4 *b4 = reinterpret_cast<const float4 *>(brow);
+            for (int j = 0; j < a.d / 4; ++j) {
+                const float4 bv = __ldg(b4 + j);
+                float t;
+                t = __fsub_rn(qrow[4 * j + 0], bv.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(qrow[4 * j + 1], bv.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(qrow[4 * j + 2], bv.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(qrow[4 * j + 3], bv.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+        } else {
+            for (int j = 0; j < a.d; ++j) {
+                float t = __fsub_rn(qrow[j], __ldg(brow + j));
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+        }
+        keys[i] = make_key(acc, id);
+    }
+    __syncwarp();
+    warp_sort_keys<NMAX>(keys, n, lane);
+
+    // certificate: every non-candidate j has S'_j <= tau, hence
+    //   true dist_j >= |x|^2 - 2 (tau + eps) / sigma^2   and the oracle's FP32 value
+    //   >= true * (1 - gamma).  Accept iff that lower bound > k-th exact distance.
+    const int m = n < a.kcap ? n : a.kcap;
+    bool ok = true;
+    if (tau > __int_as_float(0xff800000)) {
+        if (m < a.kcap) {
+            ok = false;  // cannot happen (a threshold implies >= L >= kcap candidates)
+        } else {
+            const double sigma = (double)scale_from_maxabs_bits(a.sc->maxabs_bits);
+            const double ymax = (double)__uint_as_float(a.sc->ymax_bits);
+            const double xn2 = a.qnorm64[a.q_row_begin + r];
+            const double xn = sqrt(xn2) * sigma * (1.0 + 1e-12);
+            const double u = 1.0 / 2048.0;  // fp16 unit roundoff 2^-11
+            double eps = 0.0;
+            if (a.sc->inexact)
+                eps += (2.0 * u + u * u) * xn * ymax + (double)a.d * (1.0 / 32768.0);
+            eps += (double)a.ksteps * (1.0 / 4194304.0) * (xn * ymax + 0.5 * ymax * ymax);
+            eps += ymax * ymax * (1.0 / 536870912.0);
+            const double gamma = (double)(a.d + 2) * (1.0 / 16777216.0) * 1.0001;
+            const double lb =
+                (xn2 * (1.0 - 1e-12) - 2.0 * ((double)tau + eps) / (sigma * sigma)) * (1.0 - gamma);
+            const double dk = (double)key_score(keys[a.kcap - 1]);
+            ok = lb > dk;
+        }
+    }
+
+    const size_t orow = (size_t)(q - a.out_q_begin) * a.k;
+    int first = 0;
+    if (a.self_join) {
+        if (lane == 0) {
+            a.assign[orow] = q;
+            a.dis[orow] = 0.0f;
+        }
+        first = 1;
+    }
+    for (int i = lane; i < a.k - first; i += 32) {
+        if (i < m) {
+            a.assign[orow + first + i] = (int)key_pos(keys[i]);
+            a.dis[orow + first + i] = key_score(keys[i]);
+        } else {
+            a.assign[orow + first + i] = -1;
+            a.dis[orow + first + i] = __int_as_float(0x7f800000);
+        }
+    }
+    if (!ok && lane == 0) {
+        const uint32_t p = atomicAdd(a.fb_count, 1u);
+        a.fb_rows[p] = q;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn get_encode_fn() {
+    static encode_tiled_fn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<encode_tiled_fn>(p);
+    return fn;
+}
+
+// fp16 matrix [rows x cols] row-major (row pitch = cols), box = [box_cols x box_rows]
+bool make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_cols,
+              uint32_t box_rows) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__half)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_cols * 2 == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool build_plan(int d16, TcPlan *p) {
+    p->nseg = 0;
+    int a_off = 0, b_off = 0, k = 0;
+    auto add = [&](int bytes, int fold) {
+        if (p->nseg >= TC_MAXSEG) return false;
+        TcSeg &s = p->seg[p->nseg++];
+        s.k_off = fold ? 0 : k;
+        s.bytes = bytes;
+        s.fold = fold;
+        s.a_off = a_off;
+        s.b_off = b_off;
+        a_off += TC_ROWS * bytes;
+        b_off += TC_BN * bytes;
+        if (!fold) k += bytes / 2;
+        return true;
+    };
+    int rem = d16;
+    while (rem >= 64) {
+        if (!add(128, 0)) return false;
+        rem -= 64;
+    }
+    if (rem >= 32) {
+        if (!add(64, 0)) return false;
+        rem -= 32;
+    }
+    if (rem >= 16) {
+        if (!add(32, 0)) return false;
+        rem -= 16;
+    }
+    if (!add(32, 1)) return false;
+    p->a_bytes = a_off;
+    p->b_bytes = b_off;
+    return true;
+}
+
+int pick_L(int kcap) {
+    int L = 4 * kcap;
+    L = (L + 31) / 32 * 32;
+    if (L < 32) L = 32;
+    return L;
+}
+int pick_gcap(int L) { return L <= 32 ? 128 : (L <= 64 ? 256 : 512); }
+
+template <int GCAP>
+size_t tc_smem_bytes(const TcPlan &p) {
+    return 1024 + (size_t)p.a_bytes + (size_t)TC_NSTAGE * p.b_bytes + sizeof(TcSmemTail<GCAP>);
+}
+
+struct TcLayout {
+    size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
+    int d16, L, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join, int num_sms,
+               TcLayout *lo) {
+    const int kcap = self_join ? k - 1 : k;
+    lo->d16 = (d + 15) / 16 * 16;
+    lo->L = pick_L(kcap);
+    lo->gcap = pick_gcap(lo->L);
+    lo->n_qtiles = (n_rows + TC_ROWS - 1) / TC_ROWS;
+    lo->n_btiles = (nb + TC_BN - 1) / TC_BN;
+    int nsplit = 1;
+    while (nsplit < 4 && lo->n_qtiles * nsplit < 2 * num_sms && lo->n_btiles / (nsplit * 2) >= 16)
+        nsplit *= 2;
+    lo->nsplit = nsplit;
+    lo->tiles_per_split = (lo->n_btiles + nsplit - 1) / nsplit;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 1024);
+        return o;
+    };
+    lo->scalars = take(sizeof(PrepScalars));
+    lo->xh_b = take((size_t)nb * lo->d16 * sizeof(__half));
+    lo->xh_q = self_join ? lo->xh_b : take((size_t)nq_src_rows * lo->d16 * sizeof(__half));
+    lo->fold_b = take((size_t)nb * FOLD_COLS * sizeof(__half));
+    lo->fold_a = take((size_t)TC_ROWS * FOLD_COLS * sizeof(__half));
+    lo->norm_b = take((size_t)nb * sizeof(double));
+    lo->norm_q = self_join ? lo->norm_b : take((size_t)nq_src_rows * sizeof(double));
+    lo->cand = take((size_t)n_rows * nsplit * lo->gcap * sizeof(key64_t));
+    lo->cnt = take((size_t)n_rows * nsplit * sizeof(int));
+    lo->tau = take((size_t)n_rows * nsplit * sizeof(float));
+    lo->fb_rows = take((size_t)n_rows * sizeof(int));
+    lo->total = off + 1024;
+}
+
+}  // namespace
+
+bool tc_supported(int n_rows, int nb, int d, int k, int self_join) {
+    const int kcap = self_join ? k - 1 : k;
+    if (kcap < 1 || kcap > 32) return false;
+    if (nb < 2048 || n_rows < 1) return false;
+    if (d < 1 || d > 4096) return false;
+    TcPlan p;
+    if (!build_plan((d + 15) / 16 * 16, &p)) return false;
+    const int gcap = pick_gcap(pick_L(kcap));
+    size_t smem = gcap == 128 ? tc_smem_bytes<128>(p)
+                              : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
+    return smem <= 227 * 1024;
+}
+
+size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms) {
+    TcLayout lo;
+    tc_layout(n_rows, n_rows, nb, d, k, self_join, num_sms, &lo);
+    return lo.total;
+}
+
+// Tensor-core search of query rows [q_begin, q_begin + n_rows).
+//   d_queries: self-join -> same matrix as d_base (row q is query q);
+//              otherwise a matrix whose row (q - q_row0) is query q.
+// Rows that fail the certificate are written to *h_fb_count / d_fb_rows (absolute ids);
+// the caller redoes them with the exact kernel.  Synchronises the stream once.
+cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row0, int q_begin,
+                          int out_q_begin, int n_rows, int nb, int d, int k, int self_join,
+                          int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
+                          int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
+                          unsigned *h_fb_count) {
+    *h_fb_count = 0;
+    if (n_rows <= 0) return cudaSuccess;
+    const int kcap = self_join ? k - 1 : k;
+    TcLayout lo;
+    tc_layout(n_rows, n_rows, nb, d, k, self_join, num_sms, &lo);
+    if (lo.total > work_bytes) return cudaErrorMemoryAllocation;
+    unsigned char *w = reinterpret_cast<unsigned char *>(
+        ((uintptr_t)d_work + 1023) & ~(uintptr_t)1023);
+    PrepScalars *sc = reinterpret_cast<PrepScalars *>(w + lo.scalars);
+    __half *xh_b = reinterpret_cast<__half *>(w + lo.xh_b);
+    __half *xh_q = reinterpret_cast<__half *>(w + lo.xh_q);
+    __half *fold_b = reinterpret_cast<__half *>(w + lo.fold_b);
+    __half *fold_a = reinterpret_cast<__half *>(w + lo.fold_a);
+    double *norm_b = reinterpret_cast<double *>(w + lo.norm_b);
+    double *norm_q = reinterpret_cast<double *>(w + lo.norm_q);
+    key64_t *cand = reinterpret_cast<key64_t *>(w + lo.cand);
+    int *cnt = reinterpret_cast<int *>(w + lo.cnt);
+    float *tau = reinterpret_cast<float *>(w + lo.tau);
+    int *fb_rows = reinterpret_cast<int *>(w + lo.fb_rows);
+    *d_fb_rows_out = fb_rows;
+
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(sc, 0, sizeof(PrepScalars), stream)) != cudaSuccess) return e;
+
+    // ---- prep ----
+    // queries of this launch: rows [q_src0, q_src0 + n_rows) of d_queries
+    const int q_src0 = self_join ? q_begin : q_begin - q_row0;
+    const int grid_ma = num_sms * 8;
+    maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_base, (size_t)nb * d, &sc->maxabs_bits);
+    ++*launches;
+    if (!self_join) {
+        maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
+                                                   (size_t)n_rows * d, &sc->maxabs_bits);
+        ++*launches;
+    }
+    prep_rows_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d16, xh_b, norm_b, fold_b,
+                                                       1, sc);
+    ++*launches;
+    if (!self_join) {
+        prep_rows_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
+                                                               n_rows, d, lo.d16, xh_q, norm_q,
+                                                               nullptr, 0, sc);
+        ++*launches;
+    }
+    fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
+    ++*launches;
+
+    // ---- tensor maps + plan ----
+    TcMaps maps;
+    TcArgs args;
+    if (!build_plan(lo.d16, &args.plan)) return cudaErrorInvalidValue;
+    const uint64_t a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
+    const uint32_t boxc[3] = {64, 32, 16};
+    for (int c = 0; c < 3; ++c) {
+        // classes a small d never uses still need a legal box
+        const uint32_t bc = boxc[c] <= (uint32_t)lo.d16 ? boxc[c] : 16;
+        if (!make_map(&maps.a[c], xh_q, a_rows, lo.d16, bc, TC_ROWS) ||
+            !make_map(&maps.b[c], xh_b, nb, lo.d16, bc, TC_BN))
+            return cudaErrorInvalidValue;
+    }
+    if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, TC_ROWS) ||
+        !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, TC_BN))
+        return cudaErrorInvalidValue;
+
+    args.n_rows = n_rows;
+    args.q_begin = q_begin;
+    args.q_op_begin = self_join ? q_begin : 0;
+    args.nb = nb;
+    args.self_join = self_join;
+    args.n_qtiles = lo.n_qtiles;
+    args.nsplit = lo.nsplit;
+    args.tiles_per_split = lo.tiles_per_split;
+    args.n_btiles = lo.n_btiles;
+    args.L = lo.L;
+    args.cand = cand;
+    args.cand_cnt = cnt;
+    args.cand_tau = tau;
+
+    const int n_items = lo.n_qtiles * lo.nsplit;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    size_t smem;
+    if (lo.gcap == 128) {
+        smem = tc_smem_bytes<128>(args.plan);
+        if ((e = cudaFuncSetAttribute(knn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)) != cudaSuccess)
+            return e;
+        knn_tc_kernel<128><<<grid, TC_THREADS, smem, stream>>>(maps, args);
+    } else if (lo.gcap == 256) {
+        smem = tc_smem_bytes<256>(args.plan);
+        if ((e = cudaFuncSetAttribute(knn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)) != cudaSuccess)
+            return e;
+        knn_tc_kernel<256><<<grid, TC_THREADS, smem, stream>>>(maps, args);
+    } else {
+        smem = tc_smem_bytes<512>(args.plan);
+        if ((e = cudaFuncSetAttribute(knn_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)) != cudaSuccess)
+            return e;
+        knn_tc_kernel<512><<<grid, TC_THREADS, smem, stream>>>(maps, args);
+    }
+    ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    // ---- re-rank + certificate ----
+    RerankArgs ra;
+    ra.base = d_base;
+    ra.queries = self_join ? d_base : d_queries;
+    ra.q_row_begin = q_src0;
+    ra.q_begin = q_begin;
+    ra.out_q_begin = out_q_begin;
+    ra.n_rows = n_rows;
+    ra.nb = nb;
+    ra.d = d;
+    ra.k = k;
+    ra.kcap = kcap;
+    ra.self_join = self_join;
+    ra.nsplit = lo.nsplit;
+    ra.gcap = lo.gcap;
+    ra.cand = cand;
+    ra.cand_cnt = cnt;
+    ra.cand_tau = tau;
+    ra.qnorm64 = self_join ? norm_b : norm_q - q_src0;  // indexed by q_row_begin + r
+    ra.sc = sc;
+    ra.ksteps = (lo.d16 + FOLD_COLS) / 16;
+    ra.assign = d_assign;
+    ra.dis = d_dis;
+    ra.fb_rows = fb_rows;
+    ra.fb_count = &sc->fb_count;
+    const int nmax = lo.gcap * lo.nsplit;
+    const int rgrid = (n_rows + RR_WARPS - 1) / RR_WARPS;
+    const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
+#define LAUNCH_RR(N)                                                                             \
+    do {                                                                                         \
+        size_t sm = (size_t)RR_WARPS * N * sizeof(key64_t) + qbytes;                             \
+        if ((e = cudaFuncSetAttribute(knn_rerank_kernel<N>,                                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) !=  \
+            cudaSuccess)                                                                         \
+            return e;                                                                            \
+        knn_rerank_kernel<N><<<rgrid, RR_WARPS * 32, sm, stream>>>(ra);                          \
+    } while (0)
+    if (nmax <= 128) LAUNCH_RR(128);
+    else if (nmax <= 256) LAUNCH_RR(256);
+    else if (nmax <= 512) LAUNCH_RR(512);
+    else if (nmax <= 1024) LAUNCH_RR(1024);
+    else LAUNCH_RR(2048);
+#undef LAUNCH_RR
+    ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    unsigned fbc = 0;
+    if ((e = cudaMemcpyAsync(&fbc, &sc->fb_count, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                             stream)) != cudaSuccess)
+        return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    *h_fb_count = fbc;
+    return cudaSuccess;
+}
+
+}  // namespace pqh

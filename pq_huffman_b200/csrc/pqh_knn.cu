@@ -195,32 +195,59 @@ int check_args(int nq_total, int nb, int d, int k, const void *b, const void *v,
     return PQH_OK;
 }
 
+size_t exact_ws(int n_rows, int nb, int k, int num_sms) {
+    (void)nb;
+    return pqh::exact_workspace_bound(n_rows, k > 1 ? k : 1, num_sms);
+}
+
+size_t align1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
+
+size_t workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms) {
+    size_t ex = exact_ws(n_rows, nb, k, num_sms);
+    if (!pqh::tc_supported(n_rows, nb, d, k, self_join)) return ex + 1024;
+    // tensor-core scratch, then room for the exact kernel on the rows it hands back
+    return align1k(pqh::tc_workspace_bytes(n_rows, nb, d, k, self_join, num_sms)) + ex + 2048;
+}
+
 // Search rows [q_begin,q_end) with all pointers already on device `dc`.
-int search_on_device(DeviceCtx &dc, int algo, int nq_total, int nb, int d, int k,
-                     const float *d_b, const float *d_v, int self_join, int q_begin, int q_end,
+// Query q's vector is row (q - q_row0) of d_v; its output row is (q - q_begin).
+int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float *d_b,
+                     const float *d_v, int q_row0, int self_join, int q_begin, int q_end,
                      int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
                      cudaStream_t stream, pqh_knn_stats_t *st) {
-    (void)nq_total;
-    (void)algo;
     const int n_rows = q_end - q_begin;
     if (n_rows <= 0 || k <= 0) return PQH_OK;
     int launches = 0;
-    CU_TRY(pqh::launch_knn_exact(d_b, d_v, nullptr, q_begin, q_begin, n_rows, nb, d, k, self_join,
-                                 d_assign, d_dis, d_work, work_bytes, dc.num_sms, stream,
-                                 &launches));
+    long long rows_tc = 0, rows_ex = 0;
+    if (algo == PQH_ALGO_AUTO && pqh::tc_supported(n_rows, nb, d, k, self_join)) {
+        const size_t tcb = align1k(pqh::tc_workspace_bytes(n_rows, nb, d, k, self_join, dc.num_sms));
+        if (tcb > work_bytes) return fail(PQH_EINVAL, "workspace too small");
+        int *d_fb_rows = nullptr;
+        unsigned n_fb = 0;
+        CU_TRY(pqh::launch_knn_tc(d_b, d_v, q_row0, q_begin, q_begin, n_rows, nb, d, k, self_join,
+                                  d_assign, d_dis, d_work, tcb, dc.num_sms, stream, &launches,
+                                  &d_fb_rows, &n_fb));
+        rows_tc = n_rows - (long long)n_fb;
+        if (n_fb > 0) {
+            rows_ex = n_fb;
+            CU_TRY(pqh::launch_knn_exact(d_b, d_v, d_fb_rows, 0, q_row0, q_begin, (int)n_fb, nb, d,
+                                         k, self_join, d_assign, d_dis,
+                                         static_cast<unsigned char *>(d_work) + tcb,
+                                         work_bytes - tcb, dc.num_sms, stream, &launches));
+        }
+    } else {
+        rows_ex = n_rows;
+        CU_TRY(pqh::launch_knn_exact(d_b, d_v, nullptr, q_begin, q_row0, q_begin, n_rows, nb, d, k,
+                                     self_join, d_assign, d_dis, d_work, work_bytes, dc.num_sms,
+                                     stream, &launches));
+    }
     if (st) {
         st->rows += n_rows;
-        st->rows_exact += n_rows;
+        st->rows_tensor += rows_tc;
+        st->rows_exact += rows_ex;
         st->launches += launches;
     }
     return PQH_OK;
-}
-
-size_t workspace_bytes(int n_rows, int nb, int d, int k, int num_sms) {
-    (void)d;
-    int kcap = k > 1 ? k : 1;
-    int nsplit = pqh::exact_pick_nsplit(n_rows, nb, num_sms);
-    return pqh::exact_workspace_bytes(n_rows, kcap, nsplit);
 }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
@@ -242,7 +269,7 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
     if ((rc = dc.base.ensure(base_bytes ? base_bytes : 4))) return rc;
     if ((rc = dc.assign.ensure(out_elems * sizeof(int)))) return rc;
     if ((rc = dc.dis.ensure(out_elems * sizeof(float)))) return rc;
-    const size_t wbytes = workspace_bytes(n_rows, nb, d, k, dc.num_sms);
+    const size_t wbytes = workspace_bytes(n_rows, nb, d, k, self_join, dc.num_sms);
     if ((rc = dc.work.ensure(wbytes))) return rc;
 
     CU_TRY(cudaEventRecord(dc.ev[0], dc.stream));
@@ -250,20 +277,20 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
         CU_TRY(cudaMemcpyAsync(dc.base.p, b, base_bytes, cudaMemcpyHostToDevice, dc.stream));
     const float *d_b = static_cast<const float *>(dc.base.p);
     const float *d_v = d_b;
-    int dq_begin = q_begin;
+    int q_row0 = 0;
     if (!self_join) {
-        // only the rows this call searches travel; the kernel sees them as rows [0, n_rows)
+        // only the rows this call searches travel: row (q - q_begin) of the device copy
         const size_t qbytes = (size_t)n_rows * d * sizeof(float);
         if ((rc = dc.queries.ensure(qbytes))) return rc;
         CU_TRY(cudaMemcpyAsync(dc.queries.p, v + (size_t)q_begin * d, qbytes,
                                cudaMemcpyHostToDevice, dc.stream));
         d_v = static_cast<const float *>(dc.queries.p);
-        dq_begin = 0;
+        q_row0 = q_begin;
     }
     CU_TRY(cudaEventRecord(dc.ev[1], dc.stream));
-    rc = search_on_device(dc, c->algo, nq_total, nb, d, k, d_b, d_v, self_join, dq_begin,
-                          dq_begin + n_rows, static_cast<int *>(dc.assign.p),
-                          static_cast<float *>(dc.dis.p), dc.work.p, dc.work.cap, dc.stream, st);
+    rc = search_on_device(dc, c->algo, nb, d, k, d_b, d_v, q_row0, self_join, q_begin, q_end,
+                          static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
+                          dc.work.p, dc.work.cap, dc.stream, st);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
     CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int), cudaMemcpyDeviceToHost,
@@ -378,7 +405,8 @@ int pqh_knn_search_rows(int nq_total, int nb, int d, int k, const float *b, cons
 }
 
 long long pqh_knn_workspace_bytes(int nq, int nb, int d, int k) {
-    return (long long)workspace_bytes(nq, nb, d, k, 148);
+    size_t a = workspace_bytes(nq, nb, d, k, 0, 148), b = workspace_bytes(nq, nb, d, k, 1, 148);
+    return (long long)(a > b ? a : b);
 }
 
 int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const float *d_b,
@@ -397,13 +425,13 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
     CU_TRY(cudaSetDevice(device));
     const int n_rows = q_end - q_begin;
     if (n_rows > 0 &&
-        (long long)workspace_bytes(n_rows, nb, d, k, dc->num_sms) > work_bytes)
+        (long long)workspace_bytes(n_rows, nb, d, k, self_join, dc->num_sms) > work_bytes)
         return fail(PQH_EINVAL, "workspace too small: need %zu bytes",
-                    workspace_bytes(n_rows, nb, d, k, dc->num_sms));
+                    workspace_bytes(n_rows, nb, d, k, self_join, dc->num_sms));
     pqh_knn_stats_t st;
     memset(&st, 0, sizeof(st));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dc->stream;
-    rc = search_on_device(*dc, c->algo, nq_total, nb, d, k, d_b, d_v, self_join, q_begin, q_end,
+    rc = search_on_device(*dc, c->algo, nb, d, k, d_b, d_v, 0, self_join, q_begin, q_end,
                           d_assign, d_dis, d_work, (size_t)work_bytes, s, &st);
     if (rc) return rc;
     if (!stream) CU_TRY(cudaStreamSynchronize(s));

@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- exact kNN queries/s on B200 for the workloads BASELINE.json names.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" is one whole all-pairs kNN job (every query row against the whole base).
+N > 1 is launched by torch.distributed.run, one rank per GPU: rank 0 holds the
+vectors, the base is broadcast once over NCCL (NVLink), query rows are split
+evenly over the ranks and the per-rank neighbour lists are gathered to rank 0
+(SURVEY.md 8e).  Rank 0 prints ONE JSON line:
+
+  value      queries/s with the vectors already resident in HBM (device-timed,
+             CUDA events, max over ranks)
+  e2e        queries/s through the host-pointer C ABI (pqh_knn_search_rows /
+             knn_full_thread): pinned host buffers, H2D + search + D2H inside the
+             timed region; for N > 1 also the NCCL broadcast and gather
+  roofline   the tcgen05 distance-GEMM kernel against the measured dense bf16/fp16 peak
+  cpu_baseline  the Yael-shaped CPU implementation (oracle/knn_blas.c) on a bounded
+             sample of the same workload, on this box's host cores (N == 1 only)
+
+--impl reference times that CPU implementation alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (generator, n, d, num_nn)   -- k passed to the search is num_nn + 1 (self + num_nn)
+    "sift100k": ("sift_like", 100_000, 128, 16),
+    "sift1m": ("sift_like", 1_000_000, 128, 16),
+    "gist1m": ("gist_like", 1_000_000, 960, 16),
+    "deep10m": ("deep_like", 10_000_000, 96, 32),
+}
+DESCRIPTIONS = {
+    "sift100k": "synthetic SIFT-shaped 100k x 128 fvecs, k=16, single block",
+    "sift1m": "SIFT1M-shaped 1M x 128 fvecs all-pairs kNN k=16",
+    "gist1m": "GIST1M-shaped 1M x 960 fvecs kNN k=16",
+    "deep10m": "Deep10M-shaped 10M x 96 fvecs kNN k=32",
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # under-load samples: the upper half of the SM clock readings
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_data(workload):
+    from pq_huffman_b200 import synth
+    gen, n, d, num_nn = WORKLOADS[workload]
+    return getattr(synth, gen)(n, d), num_nn + 1
+
+
+def cpu_sample(x, k, seconds_target, threads):
+    """Time the Yael-shaped CPU kNN on a bounded sample: a slice of query rows x whole base."""
+    from tests import oracle_ffi
+    blas = oracle_ffi.BlasBaseline()
+    n = x.shape[0]
+    probe = min(n, 1024)
+    t = time.perf_counter()
+    blas.knn_rows(x, None, k, 0, probe, n_thread=threads)
+    dt = max(time.perf_counter() - t, 1e-6)
+    rows = int(min(n, max(probe, probe * seconds_target / dt)))
+    rows = max(threads, rows // threads * threads)
+    t = time.perf_counter()
+    blas.knn_rows(x, None, k, 0, rows, n_thread=threads)
+    dt = time.perf_counter() - t
+    return rows / dt, rows, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (Yael-shaped stand-in), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    x, k = make_data(args.workload)
+    threads = os.cpu_count() or 1
+    n, d = x.shape
+    per_step = max(2.0, min(30.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals, rows_used = [], 0
+    for i in range(args.warmup + args.steps):
+        qps, rows, dt = cpu_sample(x, k, per_step, threads)
+        if i >= args.warmup:
+            vals.append((rows, dt))
+        rows_used = rows
+    tot_rows = sum(r for r, _ in vals)
+    tot_dt = sum(t for _, t in vals)
+    qps = tot_rows / tot_dt
+    sample = (f"{rows_used} query rows x full {n}-row base per step (of {n} rows), "
+              f"linear in query rows")
+    line = {
+        "impl": "reference", "metric": "exact kNN queries/sec", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * n / qps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": DESCRIPTIONS[args.workload], "n": n, "d": d, "k": k - 1,
+                   "inputs": "host"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": sample,
+                         "note": "Yael v438 is not vendored/installed; oracle/knn_blas.c restates "
+                                 "its sgemm + per-query heap algorithm on scipy's OpenBLAS"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pq_huffman_b200 import knn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    knn.init([local])
+
+    gen, n, d, num_nn = WORKLOADS[args.workload]
+    k = num_nn + 1
+    per = (n + world - 1) // world
+    q_lo, q_hi = min(n, rank * per), min(n, (rank + 1) * per)
+    rows = q_hi - q_lo
+
+    # ---- data: rank 0 generates, pinned; the other ranks only receive the broadcast ----
+    host_x = None
+    if rank == 0:
+        x_np, _ = make_data(args.workload)
+        host_x = torch.from_numpy(x_np).pin_memory()
+        del x_np
+    d_x = torch.empty((n, d), dtype=torch.float32, device=dev)
+    if rank == 0:
+        d_x.copy_(host_x, non_blocking=True)
+    if world > 1:
+        dist.broadcast(d_x, src=0)
+    torch.cuda.synchronize()
+
+    d_assign = torch.empty((max(rows, 1), k), dtype=torch.int32, device=dev)
+    d_dis = torch.empty((max(rows, 1), k), dtype=torch.float32, device=dev)
+    wbytes = knn.workspace_bytes(max(rows, 1), n, d, k)
+    d_work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    # a real (non-null) stream: the library runs its kernels on the handle it is given, and
+    # torch.cuda.Event only sees work on the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+
+    def device_step():
+        knn.search_device(local, n, n, d, k, d_x.data_ptr(), d_x.data_ptr(), True, q_lo, q_hi,
+                          d_assign.data_ptr(), d_dis.data_ptr(), d_work.data_ptr(), wbytes,
+                          stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed arm ----
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gemm_ms, launches, st_acc = 0.0, 0, None
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+        st = knn.last_stats()
+        gemm_ms += st["ms_gemm"]
+        launches += st["launches"]
+        st_acc = st
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms, gemm_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, gemm_ms_max = float(t[0]), float(t[1])
+    value = n * args.steps / (ms_max / 1e3)
+
+    # ---- end-to-end arm: host pointers through the C ABI ----
+    out_a = torch.empty((max(rows, 1), k), dtype=torch.int32).pin_memory()
+    out_d = torch.empty((max(rows, 1), k), dtype=torch.float32).pin_memory()
+    if world > 1:
+        gat_a = [torch.empty((per, k), dtype=torch.int32, device=dev) for _ in range(world)] \
+            if rank == 0 else None
+        gat_d = [torch.empty((per, k), dtype=torch.float32, device=dev) for _ in range(world)] \
+            if rank == 0 else None
+        pad_a = torch.zeros((per, k), dtype=torch.int32, device=dev)
+        pad_d = torch.zeros((per, k), dtype=torch.float32, device=dev)
+        full_a = torch.empty((per * world, k), dtype=torch.int32).pin_memory() if rank == 0 else None
+        full_d = torch.empty((per * world, k), dtype=torch.float32).pin_memory() if rank == 0 \
+            else None
+
+    def e2e_step():
+        if world == 1:
+            # the call a user of the reference makes: host buffers in, host results out
+            import ctypes  # noqa: F401
+            lib_rows = knn._lib.load().pqh_knn_search_rows
+            rc = lib_rows(n, n, d, k, host_x.data_ptr(), host_x.data_ptr(), 1, 0, n,
+                          out_a.data_ptr(), out_d.data_ptr())
+            if rc:
+                raise RuntimeError(knn._lib.load().pqh_last_error().decode())
+        else:
+            if rank == 0:
+                d_x.copy_(host_x, non_blocking=True)          # H2D of this step's input
+            dist.broadcast(d_x, src=0)                          # base over NVLink
+            device_step()
+            pad_a[:rows].copy_(d_assign[:rows])
+            pad_d[:rows].copy_(d_dis[:rows])
+            dist.gather(pad_a, gat_a, dst=0)
+            dist.gather(pad_d, gat_d, dst=0)
+            if rank == 0:
+                for r in range(world):                          # D2H of the step's result
+                    full_a[r * per:(r + 1) * per].copy_(gat_a[r], non_blocking=True)
+                    full_d[r * per:(r + 1) * per].copy_(gat_d[r], non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n * e2e_steps / float(te[0])
+    e2e_stats = knn.last_stats() if world == 1 else None
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        flops_per_launch = 2.0 * rows * n * d          # algorithmic: 2*Nb*d per query
+        launches_gemm = args.steps
+        achieved = (flops_per_launch / (gemm_ms_max / launches_gemm / 1e3) / 1e12
+                    if gemm_ms_max > 0 else 0.0)
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload)
+        line = {
+            "metric": "exact kNN queries/sec", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16 tensor-core filter, f32 exact re-rank",
+            "data": "synthetic",
+            "config": {"workload": DESCRIPTIONS[args.workload], "n": n, "d": d, "k": num_nn,
+                       "rows_per_gpu": per, "parallelism": f"query-rows/{world}",
+                       "l2": "inputs (%.0f MB) larger than L2, no flush needed" % (n * d * 4 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": n * d * 4,
+                    "d2h_bytes_per_step": n * k * 8, "steps": e2e_steps,
+                    "ms_per_step": 1e3 * float(te[0]) / e2e_steps,
+                    "api": "pqh_knn_search_rows (host pointers, pinned)" if world == 1 else
+                           "H2D + NCCL broadcast + pqh_knn_search_device + NCCL gather + D2H"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel runs inside a "
+                                        "long step)",
+                         "ms_per_launch": gemm_ms_max / launches_gemm, "traffic": traffic},
+            "phases_ms": {key: st_acc[key] for key in ("ms_prep", "ms_gemm", "ms_rerank",
+                                                       "ms_exact")},
+            "rows_exact_fallback": st_acc["rows_exact"],
+            "candidates_per_row": st_acc["candidates"] / max(1, st_acc["rows"]),
+            "clocks": clocks,
+        }
+        if e2e_stats:
+            line["e2e"]["phases_ms"] = {key: e2e_stats[key] for key in
+                                        ("ms_h2d", "ms_kernels", "ms_d2h", "ms_total")}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            qps, srows, dt = cpu_sample(host_x.numpy(), k, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {
+                "value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                "sample": f"{srows} query rows x full {n}-row base in {dt:.1f} s "
+                          "(oracle/knn_blas.c, Yael-shaped sgemm + heaps)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="sift1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

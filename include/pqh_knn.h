@@ -122,6 +122,11 @@ typedef struct pqh_knn_stats {
     long long launches;        /* kernels launched */
     double ms_total;           /* wall time of the call, host clock */
     double ms_h2d, ms_kernels, ms_d2h; /* device-event times of the phases */
+    double ms_prep;            /* operand conversion + norms (device events) */
+    double ms_gemm;            /* the tcgen05 distance-GEMM + filter kernel alone */
+    double ms_rerank;          /* exact FP32 re-rank + certificate */
+    double ms_exact;           /* exact FP32 kernel (fallback rows or PQH_ALGO_EXACT) */
+    double candidates;         /* candidates re-ranked, summed over rows */
 } pqh_knn_stats_t;
 int pqh_knn_last_stats(pqh_knn_stats_t *out);
 

@@ -32,6 +32,11 @@ class Stats(C.Structure):
         ("ms_h2d", C.c_double),
         ("ms_kernels", C.c_double),
         ("ms_d2h", C.c_double),
+        ("ms_prep", C.c_double),
+        ("ms_gemm", C.c_double),
+        ("ms_rerank", C.c_double),
+        ("ms_exact", C.c_double),
+        ("candidates", C.c_double),
     ]
 
 

@@ -17,12 +17,17 @@ cudaError_t launch_knn_exact(const float *d_base, const float *d_queries, const 
                              size_t work_bytes, int num_sms, cudaStream_t stream, int *launches);
 
 // ---- knn_tc.cu -------------------------------------------------------------
+struct TcTimes {
+    float ms_prep = 0.f, ms_gemm = 0.f, ms_rerank = 0.f;
+    double candidates = 0.0;
+    int inexact = 0;
+};
 bool tc_supported(int n_rows, int nb, int d, int k, int self_join);
 size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms);
 cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row0, int q_begin,
                           int out_q_begin, int n_rows, int nb, int d, int k, int self_join,
                           int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
                           int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
-                          unsigned *h_fb_count);
+                          unsigned *h_fb_count, cudaEvent_t *ev, TcTimes *times);
 
 }  // namespace pqh

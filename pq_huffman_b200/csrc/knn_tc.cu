@@ -128,6 +128,7 @@ struct PrepScalars {
     uint32_t inexact;      // some fp16(sigma*x) != sigma*x
     uint32_t fb_count;     // rows that failed the certificate
     uint32_t pad[4];
+    unsigned long long cand_total[64];  // candidates re-ranked (spread to avoid contention)
 };
 
 __global__ void __launch_bounds__(256)
@@ -548,9 +549,13 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
             a.dis[orow + first + i] = __int_as_float(0x7f800000);
         }
     }
-    if (!ok && lane == 0) {
-        const uint32_t p = atomicAdd(a.fb_count, 1u);
-        a.fb_rows[p] = q;
+    if (lane == 0) {
+        atomicAdd(const_cast<unsigned long long *>(&a.sc->cand_total[blockIdx.x & 63]),
+                  (unsigned long long)n);
+        if (!ok) {
+            const uint32_t p = atomicAdd(a.fb_count, 1u);
+            a.fb_rows[p] = q;
+        }
     }
 }
 
@@ -710,7 +715,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                           int out_q_begin, int n_rows, int nb, int d, int k, int self_join,
                           int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
                           int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
-                          unsigned *h_fb_count) {
+                          unsigned *h_fb_count, cudaEvent_t *ev, TcTimes *times) {
     *h_fb_count = 0;
     if (n_rows <= 0) return cudaSuccess;
     const int kcap = self_join ? k - 1 : k;
@@ -733,6 +738,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     *d_fb_rows_out = fb_rows;
 
     cudaError_t e;
+    if (ev) cudaEventRecord(ev[0], stream);
     if ((e = cudaMemsetAsync(sc, 0, sizeof(PrepScalars), stream)) != cudaSuccess) return e;
 
     // ---- prep ----
@@ -792,6 +798,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     const int n_items = lo.n_qtiles * lo.nsplit;
     const int grid = n_items < num_sms ? n_items : num_sms;
     size_t smem;
+    if (ev) cudaEventRecord(ev[1], stream);
     if (lo.gcap == 128) {
         smem = tc_smem_bytes<128>(args.plan);
         if ((e = cudaFuncSetAttribute(knn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -813,6 +820,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     }
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (ev) cudaEventRecord(ev[2], stream);
 
     // ---- re-rank + certificate ----
     RerankArgs ra;
@@ -860,12 +868,23 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
-    unsigned fbc = 0;
-    if ((e = cudaMemcpyAsync(&fbc, &sc->fb_count, sizeof(unsigned), cudaMemcpyDeviceToHost,
-                             stream)) != cudaSuccess)
+    if (ev) cudaEventRecord(ev[3], stream);
+    PrepScalars hsc;
+    if ((e = cudaMemcpyAsync(&hsc, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost, stream)) !=
+        cudaSuccess)
         return e;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-    *h_fb_count = fbc;
+    *h_fb_count = hsc.fb_count;
+    if (times) {
+        times->candidates = 0;
+        for (int i = 0; i < 64; ++i) times->candidates += (double)hsc.cand_total[i];
+        times->inexact = (int)hsc.inexact;
+        if (ev) {
+            cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);
+            cudaEventElapsedTime(&times->ms_gemm, ev[1], ev[2]);
+            cudaEventElapsedTime(&times->ms_rerank, ev[2], ev[3]);
+        }
+    }
     return cudaSuccess;
 }
 

@@ -80,6 +80,7 @@ struct DeviceCtx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf base, queries, assign, dis, work;
 };
 
@@ -122,6 +123,8 @@ void destroy_ctx(Context *c) {
         d.dis.release();
         d.work.release();
         for (auto &e : d.ev)
+            if (e) cudaEventDestroy(e);
+        for (auto &e : d.kev)
             if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -168,6 +171,7 @@ int create_ctx(const int *devices, int n, Context **out) {
                         cudaGetErrorString(cudaGetLastError()));
         }
         for (auto &ev : d.ev) cudaEventCreate(&ev);
+        for (auto &ev : d.kev) cudaEventCreate(&ev);
         c->devs.push_back(d);
     }
     *out = c;
@@ -195,6 +199,12 @@ int check_args(int nq_total, int nb, int d, int k, const void *b, const void *v,
     return PQH_OK;
 }
 
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
 size_t exact_ws(int n_rows, int nb, int k, int num_sms) {
     (void)nb;
     return pqh::exact_workspace_bound(n_rows, k > 1 ? k : 1, num_sms);
@@ -214,32 +224,50 @@ size_t workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_
 int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float *d_b,
                      const float *d_v, int q_row0, int self_join, int q_begin, int q_end,
                      int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
-                     cudaStream_t stream, pqh_knn_stats_t *st) {
+                     cudaStream_t stream, pqh_knn_stats_t *st, bool sync_for_stats) {
     const int n_rows = q_end - q_begin;
     if (n_rows <= 0 || k <= 0) return PQH_OK;
     int launches = 0;
     long long rows_tc = 0, rows_ex = 0;
+    bool exact_timed = false;
     if (algo == PQH_ALGO_AUTO && pqh::tc_supported(n_rows, nb, d, k, self_join)) {
         const size_t tcb = align1k(pqh::tc_workspace_bytes(n_rows, nb, d, k, self_join, dc.num_sms));
         if (tcb > work_bytes) return fail(PQH_EINVAL, "workspace too small");
         int *d_fb_rows = nullptr;
         unsigned n_fb = 0;
+        pqh::TcTimes tt;
         CU_TRY(pqh::launch_knn_tc(d_b, d_v, q_row0, q_begin, q_begin, n_rows, nb, d, k, self_join,
                                   d_assign, d_dis, d_work, tcb, dc.num_sms, stream, &launches,
-                                  &d_fb_rows, &n_fb));
+                                  &d_fb_rows, &n_fb, dc.kev, &tt));
+        if (st) {
+            st->ms_prep += tt.ms_prep;
+            st->ms_gemm += tt.ms_gemm;
+            st->ms_rerank += tt.ms_rerank;
+            st->candidates += tt.candidates;
+        }
         rows_tc = n_rows - (long long)n_fb;
         if (n_fb > 0) {
             rows_ex = n_fb;
+            CU_TRY(cudaEventRecord(dc.kev[4], stream));
             CU_TRY(pqh::launch_knn_exact(d_b, d_v, d_fb_rows, 0, q_row0, q_begin, (int)n_fb, nb, d,
                                          k, self_join, d_assign, d_dis,
                                          static_cast<unsigned char *>(d_work) + tcb,
                                          work_bytes - tcb, dc.num_sms, stream, &launches));
+            CU_TRY(cudaEventRecord(dc.kev[5], stream));
+            exact_timed = true;
         }
     } else {
         rows_ex = n_rows;
+        CU_TRY(cudaEventRecord(dc.kev[4], stream));
         CU_TRY(pqh::launch_knn_exact(d_b, d_v, nullptr, q_begin, q_row0, q_begin, n_rows, nb, d, k,
                                      self_join, d_assign, d_dis, d_work, work_bytes, dc.num_sms,
                                      stream, &launches));
+        CU_TRY(cudaEventRecord(dc.kev[5], stream));
+        exact_timed = true;
+    }
+    if (exact_timed && st && sync_for_stats) {
+        CU_TRY(cudaStreamSynchronize(stream));
+        st->ms_exact += ev_ms(dc.kev[4], dc.kev[5]);
     }
     if (st) {
         st->rows += n_rows;
@@ -248,12 +276,6 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
         st->launches += launches;
     }
     return PQH_OK;
-}
-
-float ev_ms(cudaEvent_t a, cudaEvent_t b) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, a, b);
-    return ms;
 }
 
 // Host-pointer search on one device.
@@ -290,7 +312,7 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
     CU_TRY(cudaEventRecord(dc.ev[1], dc.stream));
     rc = search_on_device(dc, c->algo, nb, d, k, d_b, d_v, q_row0, self_join, q_begin, q_end,
                           static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
-                          dc.work.p, dc.work.cap, dc.stream, st);
+                          dc.work.p, dc.work.cap, dc.stream, st, false);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
     CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int), cudaMemcpyDeviceToHost,
@@ -303,6 +325,7 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
         st->ms_h2d += ev_ms(dc.ev[0], dc.ev[1]);
         st->ms_kernels += ev_ms(dc.ev[1], dc.ev[2]);
         st->ms_d2h += ev_ms(dc.ev[2], dc.ev[3]);
+        if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.kev[4], dc.kev[5]);
     }
     return PQH_OK;
 }
@@ -358,6 +381,11 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, const f
             if (sts[g].ms_h2d > st.ms_h2d) st.ms_h2d = sts[g].ms_h2d;
             if (sts[g].ms_kernels > st.ms_kernels) st.ms_kernels = sts[g].ms_kernels;
             if (sts[g].ms_d2h > st.ms_d2h) st.ms_d2h = sts[g].ms_d2h;
+            if (sts[g].ms_prep > st.ms_prep) st.ms_prep = sts[g].ms_prep;
+            if (sts[g].ms_gemm > st.ms_gemm) st.ms_gemm = sts[g].ms_gemm;
+            if (sts[g].ms_rerank > st.ms_rerank) st.ms_rerank = sts[g].ms_rerank;
+            if (sts[g].ms_exact > st.ms_exact) st.ms_exact = sts[g].ms_exact;
+            st.candidates += sts[g].candidates;
         }
     }
     st.ms_total =
@@ -432,7 +460,7 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
     memset(&st, 0, sizeof(st));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dc->stream;
     rc = search_on_device(*dc, c->algo, nb, d, k, d_b, d_v, 0, self_join, q_begin, q_end,
-                          d_assign, d_dis, d_work, (size_t)work_bytes, s, &st);
+                          d_assign, d_dis, d_work, (size_t)work_bytes, s, &st, stream == nullptr);
     if (rc) return rc;
     if (!stream) CU_TRY(cudaStreamSynchronize(s));
     c->stats = st;

@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -58,6 +59,15 @@ struct TcPlan {
     TcSeg seg[TC_MAXSEG];
 };
 
+struct PrepScalars {
+    uint32_t maxabs_bits;  // max |x| over base and queries
+    uint32_t ymax_bits;    // max scaled base norm |y'| (float bits, rounded up)
+    uint32_t inexact;      // some fp16(sigma*x) != sigma*x
+    uint32_t fb_count;     // rows that failed the certificate
+    uint32_t pad[4];
+    unsigned long long cand_total[64];  // candidates re-ranked (spread to avoid contention)
+};
+
 struct TcArgs {
     int n_rows;      // query rows in this launch
     int q_begin;     // absolute query index of row 0 (self-join: also its base position)
@@ -65,7 +75,9 @@ struct TcArgs {
     int nb;
     int self_join;
     int n_qtiles, nsplit, tiles_per_split, n_btiles;
-    int L;
+    int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
+    int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
+    const PrepScalars *sc;
     key64_t *cand;
     int *cand_cnt;
     float *cand_tau;
@@ -122,15 +134,6 @@ __global__ void __launch_bounds__(256) maxabs_kernel(const float *__restrict__ x
 }
 
 // prep 2: one warp per row: fp16 operand row, exact-ish FP64 squared norm, fold pieces
-struct PrepScalars {
-    uint32_t maxabs_bits;  // max |x| over base and queries
-    uint32_t ymax_bits;    // max scaled base norm |y'| (float bits, rounded up)
-    uint32_t inexact;      // some fp16(sigma*x) != sigma*x
-    uint32_t fb_count;     // rows that failed the certificate
-    uint32_t pad[4];
-    unsigned long long cand_total[64];  // candidates re-ranked (spread to avoid contention)
-};
-
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float *__restrict__ x, int n, int d, int d16, __half *__restrict__ xh,
                  double *__restrict__ norm64, __half *__restrict__ fold, int write_fold,
@@ -190,19 +193,58 @@ __global__ void fold_const_kernel(__half *__restrict__ fa) {
 // main kernel
 template <int GCAP>
 struct TcSmemTail {
-    key64_t scratch[TC_EPI_WARPS][GCAP];
     uint64_t a_full, a_empty;
     uint64_t b_full[TC_NSTAGE], b_empty[TC_NSTAGE];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
+// Warp-cooperative shrink of one row's candidate list (n <= GCAP keys in global memory) to
+// its L best: a 32-step binary search on the ordered score bits finds the L-th best score,
+// survivors are written back compacted (unsorted).  Returns that score's ordered bits: every
+// dropped key has a score that is not better.  No sort, no shared memory.
 template <int GCAP>
-__device__ __forceinline__ void compact_row(key64_t *sc, key64_t *list, int n, int L, int lane) {
-    for (int i = lane; i < n; i += 32) sc[i] = __ldcg(list + i);
-    warp_sort_keys<GCAP>(sc, n, lane);
-    for (int i = lane; i < L; i += 32) __stcg(list + i, sc[i]);
+__device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lane) {
+    constexpr int PER = GCAP / 32;
+    key64_t k[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int idx = i * 32 + lane;
+        k[i] = idx < n ? __ldcg(list + idx) : KEY_INF;
+    }
+    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) c += ((uint32_t)(k[i] >> 32) <= mid) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= L) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t x = lo;  // L-th smallest ordered score
+    int c_lt = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) c_lt += ((uint32_t)(k[i] >> 32) < x) ? 1 : 0;
+    c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+    int quota = L - c_lt;  // how many of the keys with score == x survive
+    __syncwarp();          // all loads done before the list is overwritten
+    int base = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t h = (uint32_t)(k[i] >> 32);
+        const unsigned eq = __ballot_sync(0xffffffffu, h == x);
+        const int eq_rank = __popc(eq & lt_mask);
+        const bool keep = (h < x) || (h == x && eq_rank < quota);
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        if (keep) __stcg(list + base + __popc(kb & lt_mask), k[i]);
+        base += __popc(kb);
+        const int taken = __popc(eq);
+        quota -= taken < quota ? taken : quota;
+    }
     __syncwarp();
+    return x;
 }
 
 template <int GCAP>
@@ -344,7 +386,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
         const int row_in_cta = g * 128 + quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        key64_t *sc = tail.scratch[e];
+        const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
         int as = 0;
         uint32_t acc_ph = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
@@ -368,45 +410,84 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 ptx::mbar_wait(&tail.acc_full[as], acc_ph);
                 ptx::tc_fence_after_sync();
                 const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
+                // id checks are only needed in the tile holding this row's own column and in
+                // the (possibly ragged) last tile
+                const int tile0 = t * TC_BN;
+                const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
+                if (args.debug_mode == 1) {
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
+                    as ^= 1;
+                    if (as == 0) acc_ph ^= 1;
+                    continue;
+                }
+                uint32_t ra[32], rb[32];
+                ptx::tmem_ld_32x32b_x32(tbase, ra);
+                ptx::tmem_wait_ld();
+                // Two chunks per trip so the register buffers alternate statically; the slow
+                // path is kept out of line (one small copy) -- the whole epilogue has to stay
+                // inside the instruction cache, it runs once per 32 accumulator columns.
 #pragma unroll 1
-                for (int c = 0; c < TC_BN / 32; ++c) {
-                    uint32_t rr[32];
-                    ptx::tmem_ld_32x32b_x32(tbase + c * 32, rr);
-                    ptx::tmem_wait_ld();
-                    float m = ptx::fmax3(__uint_as_float(rr[0]), __uint_as_float(rr[1]),
-                                         __uint_as_float(rr[2]));
+                for (int c2 = 0; c2 < TC_BN / 32; c2 += 2) {
 #pragma unroll
-                    for (int j = 3; j < 31; j += 2)
-                        m = ptx::fmax3(m, __uint_as_float(rr[j]), __uint_as_float(rr[j + 1]));
-                    m = fmaxf(m, __uint_as_float(rr[31]));
-                    const bool hit = m > tau;
-                    if (__any_sync(0xffffffffu, hit)) {
-                        if (hit) {
-                            const int col0 = t * TC_BN + c * 32;
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = c2 + h;
+                        uint32_t(&cur)[32] = h ? rb : ra;
+                        uint32_t(&nxt)[32] = h ? ra : rb;
+                        // software pipeline: chunk c+1 is in flight while chunk c is filtered
+                        if (c + 1 < TC_BN / 32) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, nxt);
+                        unsigned gmask = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float v = __uint_as_float(rr[j]);
-                                const int id = col0 + j;
-                                if (v > tau && id < ib_hi && id != self) {
-                                    __stcg(list + cnt, make_key(-v, (uint32_t)id));
-                                    ++cnt;
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const int o = q4 * 8;
+                            float m = ptx::fmax3(__uint_as_float(cur[o]), __uint_as_float(cur[o + 1]),
+                                                 __uint_as_float(cur[o + 2]));
+                            m = ptx::fmax3(m, __uint_as_float(cur[o + 3]),
+                                           __uint_as_float(cur[o + 4]));
+                            m = ptx::fmax3(m, __uint_as_float(cur[o + 5]),
+                                           __uint_as_float(cur[o + 6]));
+                            m = fmaxf(m, __uint_as_float(cur[o + 7]));
+                            gmask |= (m > tau) ? (1u << q4) : 0u;
+                        }
+                        // groups of 8 columns in which some row of this warp has a candidate
+                        unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
+                        if (groups != 0 && args.debug_mode != 2) {
+                            if (c + 1 < TC_BN / 32) ptx::tmem_wait_ld();
+                            do {
+                                const int q4 = __ffs(groups) - 1;
+                                groups &= groups - 1;
+                                uint32_t v8[8];
+                                ptx::tmem_ld_32x32b_x8(tbase + c * 32 + q4 * 8, v8);
+                                ptx::tmem_wait_ld();
+                                if (gmask & (1u << q4)) {
+                                    const int col0 = tile0 + c * 32 + q4 * 8;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float v = __uint_as_float(v8[j]);
+                                        const int id = col0 + j;
+                                        if (v > tau && (!special || (id < ib_hi && id != self))) {
+                                            __stcg(list + cnt, make_key(-v, (uint32_t)id));
+                                            ++cnt;
+                                        }
+                                    }
+                                }
+                            } while (groups != 0);
+                            unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - 32);
+                            while (need) {
+                                const int src = __ffs(need) - 1;
+                                need &= need - 1;
+                                key64_t *l = reinterpret_cast<key64_t *>(
+                                    __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+                                const int n = __shfl_sync(0xffffffffu, cnt, src);
+                                const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
+                                if (lane == src) {
+                                    cnt = L;
+                                    tau = -ordered_to_float(x);
                                 }
                             }
-                        }
-                        unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - 32);
-                        while (need) {
-                            const int src = __ffs(need) - 1;
-                            need &= need - 1;
-                            key64_t *l = reinterpret_cast<key64_t *>(
-                                __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-                            const int n = __shfl_sync(0xffffffffu, cnt, src);
-                            compact_row<GCAP>(sc, l, n, args.L, lane);
-                            const key64_t kth = sc[args.L - 1];
-                            __syncwarp();
-                            if (lane == src) {
-                                cnt = args.L;
-                                tau = -key_score(kth);
-                            }
+                        } else if (c + 1 < TC_BN / 32) {
+                            ptx::tmem_wait_ld();
                         }
                     }
                 }
@@ -632,8 +713,10 @@ bool build_plan(int d16, TcPlan *p) {
     return true;
 }
 
-int pick_L(int kcap) {
-    int L = 4 * kcap;
+// candidates kept per row: 4x the neighbours asked for when the FP16 operands are rounded
+// (slack for the certificate), 2x when they are exact (integer-valued data)
+int pick_L(int kcap, bool inexact) {
+    int L = (inexact ? 4 : 2) * kcap;
     L = (L + 31) / 32 * 32;
     if (L < 32) L = 32;
     return L;
@@ -647,7 +730,7 @@ size_t tc_smem_bytes(const TcPlan &p) {
 
 struct TcLayout {
     size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
-    int d16, L, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
+    int d16, L, L_exact, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -656,7 +739,8 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
                TcLayout *lo) {
     const int kcap = self_join ? k - 1 : k;
     lo->d16 = (d + 15) / 16 * 16;
-    lo->L = pick_L(kcap);
+    lo->L = pick_L(kcap, true);
+    lo->L_exact = pick_L(kcap, false);
     lo->gcap = pick_gcap(lo->L);
     lo->n_qtiles = (n_rows + TC_ROWS - 1) / TC_ROWS;
     lo->n_btiles = (nb + TC_BN - 1) / TC_BN;
@@ -694,7 +778,7 @@ bool tc_supported(int n_rows, int nb, int d, int k, int self_join) {
     if (d < 1 || d > 4096) return false;
     TcPlan p;
     if (!build_plan((d + 15) / 16 * 16, &p)) return false;
-    const int gcap = pick_gcap(pick_L(kcap));
+    const int gcap = pick_gcap(pick_L(kcap, true));
     size_t smem = gcap == 128 ? tc_smem_bytes<128>(p)
                               : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
     return smem <= 227 * 1024;
@@ -790,7 +874,13 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     args.nsplit = lo.nsplit;
     args.tiles_per_split = lo.tiles_per_split;
     args.n_btiles = lo.n_btiles;
-    args.L = lo.L;
+    {
+        const char *dbg = getenv("PQH_TC_DEBUG");
+        args.debug_mode = dbg ? atoi(dbg) : 0;
+    }
+    args.L_exact = lo.L_exact;
+    args.L_inexact = lo.L;
+    args.sc = sc;
     args.cand = cand;
     args.cand_cnt = cnt;
     args.cand_tau = tau;

@@ -58,9 +58,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // Blocking wait with a watchdog: a pipeline bug must end in a trap (reported as a
 // CUDA error by the next API call), never in a kernel that spins forever.
 __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000ll) {
+    // try_wait suspends the thread in hardware for a bounded time per call, so counting
+    // calls is a cheap clock: ~2^26 failed polls are many seconds
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {
             printf("libpqh_knn: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
@@ -139,6 +140,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
           "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
           "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7])
         : "r"(taddr)
         : "memory");
 }

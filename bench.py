@@ -178,7 +178,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from pq_huffman_b200 import knn
+    from pq_huffman_b200 import dist_knn, knn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,8 +196,7 @@ def run_ours(args):
 
     gen, n, d, num_nn = WORKLOADS[args.workload]
     k = num_nn + 1
-    per = (n + world - 1) // world
-    q_lo, q_hi = min(n, rank * per), min(n, (rank + 1) * per)
+    q_lo, q_hi, per = dist_knn.row_slice(n, world, rank)
     rows = q_hi - q_lo
 
     # ---- data: rank 0 generates, pinned; the other ranks only receive the broadcast ----
@@ -209,8 +208,7 @@ def run_ours(args):
     d_x = torch.empty((n, d), dtype=torch.float32, device=dev)
     if rank == 0:
         d_x.copy_(host_x, non_blocking=True)
-    if world > 1:
-        dist.broadcast(d_x, src=0)
+    dist_knn.broadcast_base(d_x, src=0)
     torch.cuda.synchronize()
 
     d_assign = torch.empty((max(rows, 1), k), dtype=torch.int32, device=dev)
@@ -260,16 +258,9 @@ def run_ours(args):
     # ---- end-to-end arm: host pointers through the C ABI ----
     out_a = torch.empty((max(rows, 1), k), dtype=torch.int32).pin_memory()
     out_d = torch.empty((max(rows, 1), k), dtype=torch.float32).pin_memory()
-    if world > 1:
-        gat_a = [torch.empty((per, k), dtype=torch.int32, device=dev) for _ in range(world)] \
-            if rank == 0 else None
-        gat_d = [torch.empty((per, k), dtype=torch.float32, device=dev) for _ in range(world)] \
-            if rank == 0 else None
-        pad_a = torch.zeros((per, k), dtype=torch.int32, device=dev)
-        pad_d = torch.zeros((per, k), dtype=torch.float32, device=dev)
-        full_a = torch.empty((per * world, k), dtype=torch.int32).pin_memory() if rank == 0 else None
-        full_d = torch.empty((per * world, k), dtype=torch.float32).pin_memory() if rank == 0 \
-            else None
+    if world > 1 and rank == 0:
+        full_a = torch.empty((n, k), dtype=torch.int32).pin_memory()
+        full_d = torch.empty((n, k), dtype=torch.float32).pin_memory()
 
     def e2e_step():
         if world == 1:
@@ -281,18 +272,15 @@ def run_ours(args):
             if rc:
                 raise RuntimeError(knn._lib.load().pqh_last_error().decode())
         else:
-            if rank == 0:
-                d_x.copy_(host_x, non_blocking=True)          # H2D of this step's input
-            dist.broadcast(d_x, src=0)                          # base over NVLink
-            device_step()
-            pad_a[:rows].copy_(d_assign[:rows])
-            pad_d[:rows].copy_(d_dis[:rows])
-            dist.gather(pad_a, gat_a, dst=0)
-            dist.gather(pad_d, gat_d, dst=0)
-            if rank == 0:
-                for r in range(world):                          # D2H of the step's result
-                    full_a[r * per:(r + 1) * per].copy_(gat_a[r], non_blocking=True)
-                    full_d[r * per:(r + 1) * per].copy_(gat_d[r], non_blocking=True)
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    d_x.copy_(host_x, non_blocking=True)        # H2D of this step's input
+                dist_knn.broadcast_base(d_x, src=0)             # base over NVLink (NCCL)
+                device_step()
+                ga, gd = dist_knn.gather_rows(d_assign, d_dis, n, k, dst=0)   # NCCL gather
+                if rank == 0:                                   # D2H of the step's result
+                    full_a.copy_(ga, non_blocking=True)
+                    full_d.copy_(gd, non_blocking=True)
             torch.cuda.synchronize()
 
     e2e_steps = max(1, min(args.steps, 3))

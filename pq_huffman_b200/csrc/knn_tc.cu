@@ -38,7 +38,7 @@ namespace {
 
 constexpr int TC_ROWS = 256;    // query rows per CTA: two M=128 accumulator tiles
 constexpr int TC_BN = 128;      // base rows per tile (UMMA N)
-constexpr int TC_NSTAGE = 3;    // B-tile ring
+constexpr int TC_NSTAGE = 4;    // B-tile ring
 constexpr int TC_MAXSEG = 6;
 constexpr int TC_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_EPI_WARPS = 8;

@@ -30,4 +30,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                           int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
                           unsigned *h_fb_count, cudaEvent_t *ev, TcTimes *times);
 
+// ---- knn_tc3.cu (CTA-pair kernel; plan/maps/args are the structs of knn_tc_common.cuh) ----
+int tc3_pick_nstage(const void *plan);
+cudaError_t launch_tc3(const void *maps, const void *args, int gcap, int n_items, int num_sms,
+                       cudaStream_t stream);
+
 }  // namespace pqh

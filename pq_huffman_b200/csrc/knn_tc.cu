@@ -31,85 +31,11 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
+#include "knn_tc_common.cuh"
 
 namespace pqh {
 
 namespace {
-
-constexpr int TC_ROWS = 256;    // query rows per CTA: two M=128 accumulator tiles
-constexpr int TC_BN = 128;      // base rows per tile (UMMA N)
-constexpr int TC_NSTAGE = 4;    // B-tile ring
-constexpr int TC_MAXSEG = 6;
-constexpr int TC_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_EPI_WARPS = 8;
-constexpr int FOLD_COLS = 16;
-
-struct TcSeg {
-    int k_off;   // element offset in the fp16 operand row (data segments)
-    int bytes;   // row bytes of this K segment: 128 / 64 / 32 (= swizzle span)
-    int fold;    // 1: the |y|^2 fold segment (separate tensors)
-    int a_off;   // byte offset inside the A region
-    int b_off;   // byte offset inside one B stage
-};
-
-struct TcPlan {
-    int nseg;
-    int a_bytes;  // A region bytes (256 rows)
-    int b_bytes;  // one B stage (128 rows)
-    TcSeg seg[TC_MAXSEG];
-};
-
-struct PrepScalars {
-    uint32_t maxabs_bits;  // max |x| over base and queries
-    uint32_t ymax_bits;    // max scaled base norm |y'| (float bits, rounded up)
-    uint32_t inexact;      // some fp16(sigma*x) != sigma*x
-    uint32_t fb_count;     // rows that failed the certificate
-    uint32_t pad[4];
-    unsigned long long cand_total[64];  // candidates re-ranked (spread to avoid contention)
-};
-
-struct TcArgs {
-    int n_rows;      // query rows in this launch
-    int q_begin;     // absolute query index of row 0 (self-join: also its base position)
-    int q_op_begin;  // row of row 0 inside the A operand tensor
-    int nb;
-    int self_join;
-    int n_qtiles, nsplit, tiles_per_split, n_btiles;
-    int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
-    int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
-    const PrepScalars *sc;
-    key64_t *cand;
-    int *cand_cnt;
-    float *cand_tau;
-    TcPlan plan;
-};
-
-struct TcMaps {
-    CUtensorMap a[3];  // data operand, box 256 rows: SW128 / SW64 / SW32
-    CUtensorMap b[3];  // data operand, box 128 rows
-    CUtensorMap fa;    // fold constants [256 x 16]
-    CUtensorMap fb;    // fold pieces    [nb x 16]
-};
-
-__device__ __forceinline__ int seg_class(int bytes) { return bytes == 128 ? 0 : (bytes == 64 ? 1 : 2); }
-__device__ __forceinline__ uint32_t seg_layout(int bytes) {
-    return bytes == 128 ? 2u : (bytes == 64 ? 4u : 6u);
-}
-
-// power-of-two scale putting maxabs in [2^7, 2^8)
-__host__ __device__ __forceinline__ float scale_from_maxabs_bits(uint32_t bits) {
-    int e = (int)((bits >> 23) & 0xff) - 127;  // maxabs in [2^e, 2^(e+1))
-    if ((bits & 0x7fffffffu) == 0 || e < -100) return 1.0f;
-    int se = 7 - e;
-    if (se > 100) se = 100;
-    if (se < -100) se = -100;
-    uint32_t sb = (uint32_t)(se + 127) << 23;
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(sb);
-#else
-    union { uint32_t u; float f; } c; c.u = sb; return c.f;
-#endif
-}
 
 // ------------------------------------------------------------------------------------
 // prep 1: max |x| over a matrix (grid-stride, float4), atomicMax on the IEEE bits
@@ -199,52 +125,123 @@ struct TcSmemTail {
     uint32_t tmem_base;
 };
 
-// Warp-cooperative shrink of one row's candidate list (n <= GCAP keys in global memory) to
-// its L best: a 32-step binary search on the ordered score bits finds the L-th best score,
-// survivors are written back compacted (unsorted).  Returns that score's ordered bits: every
-// dropped key has a score that is not better.  No sort, no shared memory.
+// Predicated append of (ordered(-score), id) to a row's candidate list: no branch.
+__device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint32_t score_bits,
+                                          int id) {
+    const uint32_t u = score_bits ^ 0x80000000u;                          // bits of -score
+    const uint32_t hi = u ^ ((uint32_t)((int)u >> 31) | 0x80000000u);     // float_to_ordered
+    const key64_t key = ((key64_t)hi << 32) | (key64_t)(uint32_t)id;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "@q st.global.cg.b64 [%1], %2;\n\t"
+        "}\n"
+        :
+        : "r"((int)p), "l"(list + cnt), "l"(key)
+        : "memory");
+    cnt += p ? 1 : 0;
+}
+
+// Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
+// it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
+// A thread keeps its row's running threshold tau and appends every score above it to the row's
+// candidate list; full lists are shrunk to the L best (shrink_row) and tau raised.
+// tau_shared (pair kernel): ordered bits of the threshold shared by the two threads that
+// filter the two column halves of the same row.
 template <int GCAP>
-__device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lane) {
-    constexpr int PER = GCAP / 32;
-    key64_t k[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int idx = i * 32 + lane;
-        k[i] = idx < n ? __ldcg(list + idx) : KEY_INF;
-    }
-    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
+                                            int self, int L, int lane, int debug_mode,
+                                            uint32_t *tau_shared, float &tau, int &cnt,
+                                            key64_t *list, unsigned (&ctr)[4]) {
+    const int trigger = GCAP - 32;  // hard limit; soft shrinks happen in idle time
+    const int id_lim = special ? ib_hi : 0x7fffffff;
+    // One chunk of 32 columns at a time, single register buffer, loop not unrolled: the other
+    // epilogue warp of the scheduler hides the TMEM latency, and the slow path exists once and
+    // scans the registers directly (no TMEM re-read, small code).
 #pragma unroll 1
-    for (int it = 0; it < 32; ++it) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        int c = 0;
+    for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t cur[32];
+        ptx::tmem_ld_32x32b_x32(tbase + c * 32, cur);
+        ptx::tmem_wait_ld();
+        unsigned gmask = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) c += ((uint32_t)(k[i] >> 32) <= mid) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= L) hi = mid; else lo = mid + 1;
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int o = q4 * 8;
+            float m = ptx::fmax3(__uint_as_float(cur[o]), __uint_as_float(cur[o + 1]),
+                                 __uint_as_float(cur[o + 2]));
+            m = ptx::fmax3(m, __uint_as_float(cur[o + 3]), __uint_as_float(cur[o + 4]));
+            m = ptx::fmax3(m, __uint_as_float(cur[o + 5]), __uint_as_float(cur[o + 6]));
+            m = fmaxf(m, __uint_as_float(cur[o + 7]));
+            gmask |= (m > tau) ? (1u << q4) : 0u;
+        }
+        // groups of 8 columns in which some row of this warp has a candidate
+        const unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
+        if (groups != 0 && debug_mode != 2) {
+            ++ctr[0];
+            const int col0 = col_base + c * 32;
+            // Branch-free scan of the flagged groups: divergent branches cost ~25 cycles each
+            // on this path, a predicated store costs one issue slot.
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                if (groups & (1u << q4)) {  // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t u = cur[q4 * 8 + j];
+                        const int id = col0 + q4 * 8 + j;
+                        const bool p = (__uint_as_float(u) > tau) & (id < id_lim) & (id != self);
+                        append_if(p, list, cnt, u, id);
+                    }
+                }
+            }
+            unsigned need = __ballot_sync(0xffffffffu, cnt > trigger);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                key64_t *l = reinterpret_cast<key64_t *>(
+                    __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+                const int n = __shfl_sync(0xffffffffu, cnt, src);
+                const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
+                ++ctr[1];
+                if (lane == src) {
+                    cnt = L;
+                    tau = fmaxf(tau, -ordered_to_float(x));
+                    if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
+                }
+            }
+        }
     }
-    const uint32_t x = lo;  // L-th smallest ordered score
-    int c_lt = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) c_lt += ((uint32_t)(k[i] >> 32) < x) ? 1 : 0;
-    c_lt = __reduce_add_sync(0xffffffffu, c_lt);
-    int quota = L - c_lt;  // how many of the keys with score == x survive
-    __syncwarp();          // all loads done before the list is overwritten
-    int base = 0;
-    const unsigned lt_mask = (1u << lane) - 1u;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const uint32_t h = (uint32_t)(k[i] >> 32);
-        const unsigned eq = __ballot_sync(0xffffffffu, h == x);
-        const int eq_rank = __popc(eq & lt_mask);
-        const bool keep = (h < x) || (h == x && eq_rank < quota);
-        const unsigned kb = __ballot_sync(0xffffffffu, keep);
-        if (keep) __stcg(list + base + __popc(kb & lt_mask), k[i]);
-        base += __popc(kb);
-        const int taken = __popc(eq);
-        quota -= taken < quota ? taken : quota;
+}
+
+// While the tensor cores have not finished the next accumulator tile, use the idle time to
+// shrink lists that have grown past 2L: the threshold then stays fresh without a shrink ever
+// standing between a finished accumulator stage and its release (mandatory shrinks at the hard
+// capacity GCAP-32 remain in filter_tile, but become rare).
+template <int GCAP>
+__device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
+                                                           int lane, uint32_t *tau_shared,
+                                                           float &tau, int &cnt, key64_t *list,
+                                                           unsigned (&ctr)[4]) {
+    const int soft = (2 * L < GCAP - 32) ? 2 * L : GCAP - 32;
+    while (!ptx::mbar_test_wait(bar, parity)) {
+        const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
+        if (need == 0) {
+            ptx::mbar_wait(bar, parity);
+            return;
+        }
+        const int src = __ffs(need) - 1;
+        key64_t *l = reinterpret_cast<key64_t *>(
+            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+        const int n = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t x = (GCAP > 128 && n <= 128) ? shrink_row<128>(l, n, L, lane)
+                                                    : shrink_row<GCAP>(l, n, L, lane);
+        ++ctr[2];
+        if (lane == src) {
+            cnt = L;
+            tau = fmaxf(tau, -ordered_to_float(x));
+            if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
+        }
     }
-    __syncwarp();
-    return x;
 }
 
 template <int GCAP>
@@ -389,6 +386,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
         int as = 0;
         uint32_t acc_ph = 0;
+        unsigned ctr[4] = {0, 0, 0, 0};
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int qt = item / args.nsplit, sp = item % args.nsplit;
@@ -407,90 +405,18 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             const int ib_hi = (int)b_hi;
 
             for (int t = t_lo; t < t_hi; ++t) {
-                ptx::mbar_wait(&tail.acc_full[as], acc_ph);
+                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
+                                                 cnt, list, ctr);
                 ptx::tc_fence_after_sync();
                 const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
                 // id checks are only needed in the tile holding this row's own column and in
                 // the (possibly ragged) last tile
                 const int tile0 = t * TC_BN;
                 const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
-                if (args.debug_mode == 1) {
-                    ptx::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
-                    as ^= 1;
-                    if (as == 0) acc_ph ^= 1;
-                    continue;
-                }
-                uint32_t ra[32], rb[32];
-                ptx::tmem_ld_32x32b_x32(tbase, ra);
-                ptx::tmem_wait_ld();
-                // Two chunks per trip so the register buffers alternate statically; the slow
-                // path is kept out of line (one small copy) -- the whole epilogue has to stay
-                // inside the instruction cache, it runs once per 32 accumulator columns.
-#pragma unroll 1
-                for (int c2 = 0; c2 < TC_BN / 32; c2 += 2) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c = c2 + h;
-                        uint32_t(&cur)[32] = h ? rb : ra;
-                        uint32_t(&nxt)[32] = h ? ra : rb;
-                        // software pipeline: chunk c+1 is in flight while chunk c is filtered
-                        if (c + 1 < TC_BN / 32) ptx::tmem_ld_32x32b_x32(tbase + (c + 1) * 32, nxt);
-                        unsigned gmask = 0;
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const int o = q4 * 8;
-                            float m = ptx::fmax3(__uint_as_float(cur[o]), __uint_as_float(cur[o + 1]),
-                                                 __uint_as_float(cur[o + 2]));
-                            m = ptx::fmax3(m, __uint_as_float(cur[o + 3]),
-                                           __uint_as_float(cur[o + 4]));
-                            m = ptx::fmax3(m, __uint_as_float(cur[o + 5]),
-                                           __uint_as_float(cur[o + 6]));
-                            m = fmaxf(m, __uint_as_float(cur[o + 7]));
-                            gmask |= (m > tau) ? (1u << q4) : 0u;
-                        }
-                        // groups of 8 columns in which some row of this warp has a candidate
-                        unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
-                        if (groups != 0 && args.debug_mode != 2) {
-                            if (c + 1 < TC_BN / 32) ptx::tmem_wait_ld();
-                            do {
-                                const int q4 = __ffs(groups) - 1;
-                                groups &= groups - 1;
-                                uint32_t v8[8];
-                                ptx::tmem_ld_32x32b_x8(tbase + c * 32 + q4 * 8, v8);
-                                ptx::tmem_wait_ld();
-                                if (gmask & (1u << q4)) {
-                                    const int col0 = tile0 + c * 32 + q4 * 8;
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float v = __uint_as_float(v8[j]);
-                                        const int id = col0 + j;
-                                        if (v > tau && (!special || (id < ib_hi && id != self))) {
-                                            __stcg(list + cnt, make_key(-v, (uint32_t)id));
-                                            ++cnt;
-                                        }
-                                    }
-                                }
-                            } while (groups != 0);
-                            unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - 32);
-                            while (need) {
-                                const int src = __ffs(need) - 1;
-                                need &= need - 1;
-                                key64_t *l = reinterpret_cast<key64_t *>(
-                                    __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-                                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                                const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
-                                if (lane == src) {
-                                    cnt = L;
-                                    tau = -ordered_to_float(x);
-                                }
-                            }
-                        } else if (c + 1 < TC_BN / 32) {
-                            ptx::tmem_wait_ld();
-                        }
-                    }
-                }
+                if (args.debug_mode != 1)
+                    filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
+                                      args.debug_mode, nullptr, tau, cnt, list, ctr);
+                ctr[3] += TC_BN / 32;
                 ptx::tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
@@ -502,11 +428,251 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 args.cand_tau[slot] = tau;
             }
         }
+        if (lane == 0) {
+            PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
+            for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
+        }
     }
 
     ptx::tc_fence_before_sync();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------
+// Pair kernel: two CTAs of one cluster (one TPC) run tcgen05.mma.cta_group::2.  The pair owns
+// 256 query rows (each CTA: 128, its M half, A operand resident) and sweeps the base in tiles of
+// 256 rows; each CTA TMA-loads only ITS 128-row half of a base tile and the tensor cores of both
+// SMs consume both halves.  Versus the single-CTA kernel this halves the shared-memory operand
+// traffic per MMA (the single-CTA M=128,N=128 shape needs the full 128 B/cycle of shared memory
+// for operands alone) at the same L2 traffic per SM.
+// Synchronisation: "full" barriers live in the leader CTA (rank 0) and count the TMA bytes of
+// both CTAs; "empty"/"accumulator full" barriers are per CTA and are signalled by multicast
+// tcgen05.commit; "accumulator empty" lives in the leader and is arrived on remotely by the
+// epilogue warps of both CTAs.
+constexpr int TC2_NSTAGE = 4;
+
+template <int GCAP>
+struct Tc2SmemTail {
+    uint64_t a_full, a_empty;
+    uint64_t b_full[TC2_NSTAGE], b_empty[TC2_NSTAGE];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tau_shared[128];
+    uint32_t tmem_base;
+};
+
+template <int GCAP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const TcPlan &plan = args.plan;  // a_off/a_bytes are for 256 rows: this kernel uses half
+    const int a_bytes = plan.a_bytes / 2;
+    uint8_t *smA = smem;
+    uint8_t *smB = smA + a_bytes;
+    Tc2SmemTail<GCAP> &tail =
+        *reinterpret_cast<Tc2SmemTail<GCAP> *>(smB + TC2_NSTAGE * plan.b_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 3; ++i) {
+            ptx::prefetch_tmap(&maps.a[i]);
+            ptx::prefetch_tmap(&maps.b[i]);
+        }
+        ptx::prefetch_tmap(&maps.fa);
+        ptx::prefetch_tmap(&maps.fb);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(&tail.a_full, 1);
+        ptx::mbar_init(&tail.a_empty, 1);
+        for (int i = 0; i < TC2_NSTAGE; ++i) {
+            ptx::mbar_init(&tail.b_full[i], 1);
+            ptx::mbar_init(&tail.b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tail.acc_full[i], 1);
+            ptx::mbar_init(&tail.acc_empty[i], 2 * TC_EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc_2sm<512>(&tail.tmem_base);
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::cluster_sync_all();  // barriers of both CTAs initialised before any remote signal
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = tail.tmem_base;
+
+    const int n_items = args.n_qtiles * args.nsplit;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, own halves) =====================
+        if (ptx::elect_one()) {
+            const uint32_t a_full_l = ptx::mapa_u32(ptx::smem_u32(&tail.a_full), 0);
+            int stage = 0;
+            uint32_t ph = 0, a_ph = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int qt = item / args.nsplit, sp = item % args.nsplit;
+                int t_lo = sp * args.tiles_per_split;
+                int t_hi = t_lo + args.tiles_per_split;
+                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
+                if (leader) ptx::mbar_arrive_expect_tx(&tail.a_full, 2 * a_bytes);
+                for (int s = 0; s < plan.nseg; ++s) {
+                    const TcSeg &sg = plan.seg[s];
+                    if (sg.fold)
+                        ptx::tma_load_2d_2sm(smA + sg.a_off / 2, &maps.fa, a_full_l, 0, 0);
+                    else
+                        ptx::tma_load_2d_2sm(smA + sg.a_off / 2, &maps.a[seg_class(sg.bytes)],
+                                             a_full_l, sg.k_off,
+                                             args.q_op_begin + qt * TC_ROWS + (int)rank * 128);
+                }
+                a_ph ^= 1;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    ptx::mbar_wait(&tail.b_empty[stage], ph ^ 1);
+                    if (leader) ptx::mbar_arrive_expect_tx(&tail.b_full[stage], 2 * plan.b_bytes);
+                    const uint32_t b_full_l = ptx::mapa_u32(ptx::smem_u32(&tail.b_full[stage]), 0);
+                    uint8_t *dst = smB + stage * plan.b_bytes;
+                    const int row0 = t * 256 + (int)rank * 128;
+                    for (int s = 0; s < plan.nseg; ++s) {
+                        const TcSeg &sg = plan.seg[s];
+                        if (sg.fold)
+                            ptx::tma_load_2d_2sm(dst + sg.b_off, &maps.fb, b_full_l, 0, row0);
+                        else
+                            ptx::tma_load_2d_2sm(dst + sg.b_off, &maps.b[seg_class(sg.bytes)],
+                                                 b_full_l, sg.k_off, row0);
+                    }
+                    if (++stage == TC2_NSTAGE) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(256, 256);
+            int stage = 0, as = 0;
+            uint32_t ph = 0, acc_ph = 0, a_ph = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int sp = item % args.nsplit;
+                int t_lo = sp * args.tiles_per_split;
+                int t_hi = t_lo + args.tiles_per_split;
+                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                ptx::mbar_wait(&tail.a_full, a_ph);
+                a_ph ^= 1;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    ptx::mbar_wait(&tail.b_full[stage], ph);
+                    ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
+                    const uint32_t a_base = ptx::smem_u32(smA);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+                    uint32_t acc = 0;
+                    for (int s = 0; s < plan.nseg; ++s) {
+                        const TcSeg &sg = plan.seg[s];
+                        const uint32_t a_addr = a_base + sg.a_off / 2;
+                        const uint32_t b_addr = b_base + sg.b_off;
+                        const uint32_t sbo = 8 * sg.bytes, lay = seg_layout(sg.bytes);
+                        for (int kk = 0; kk < sg.bytes / 32; ++kk) {
+                            ptx::umma_f16_2sm(d_tmem, ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
+                                              ptx::make_smem_desc(b_addr + kk * 32, sbo, lay), idesc,
+                                              acc);
+                            acc = 1;
+                        }
+                    }
+                    ptx::umma_commit_2sm(&tail.b_empty[stage]);
+                    ptx::umma_commit_2sm(&tail.acc_full[as]);
+                    if (++stage == TC2_NSTAGE) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                    as ^= 1;
+                    if (as == 0) acc_ph ^= 1;
+                }
+                ptx::umma_commit_2sm(&tail.a_empty);
+            }
+        }
+    } else {
+        // ===================== epilogue: threshold filter =====================
+        const int e = warp - 2;
+        const int half = e >> 2;    // which 128 of the tile's 256 columns this warp filters
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int row_in_cta = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        // each column half keeps half of the row's L (never fewer than the neighbours asked
+        // for): the union of the two halves' best kcap always contains the row's best kcap
+        const int L_row = args.sc->inexact ? args.L_inexact : args.L_exact;
+        const int L = (L_row / 2 > args.kcap) ? L_row / 2 : args.kcap;
+        uint32_t *tau_sh = &tail.tau_shared[row_in_cta];
+        uint32_t acc_empty_l[2];
+        acc_empty_l[0] = ptx::mapa_u32(ptx::smem_u32(&tail.acc_empty[0]), 0);
+        acc_empty_l[1] = ptx::mapa_u32(ptx::smem_u32(&tail.acc_empty[1]), 0);
+        int as = 0;
+        uint32_t acc_ph = 0;
+        unsigned ctr[4] = {0, 0, 0, 0};
+        const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int qt = item / args.nsplit, sp = item % args.nsplit;
+            int t_lo = sp * args.tiles_per_split;
+            int t_hi = t_lo + args.tiles_per_split;
+            if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+            const int r = qt * TC_ROWS + (int)rank * 128 + row_in_cta;
+            const bool valid = r < args.n_rows;
+            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const size_t slot = valid ? ((size_t)r * args.nsplit + sp) * 2 + half : 0;
+            key64_t *list = args.cand + slot * GCAP;
+            float tau = valid ? NEG_INF : POS_INF;
+            int cnt = 0;
+            // the two column halves of a row share one threshold (epilogue-only named barrier
+            // orders the reset against the other half's last use in the previous item)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) *tau_sh = float_to_ordered(NEG_INF);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            long long b_hi = (long long)t_hi * 256;
+            if (b_hi > args.nb) b_hi = args.nb;
+            const int ib_hi = (int)b_hi;
+
+            for (int t = t_lo; t < t_hi; ++t) {
+                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, tau_sh, tau,
+                                                 cnt, list, ctr);
+                ptx::tc_fence_after_sync();
+                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + half * 128);
+                const int tile0 = t * 256;
+                const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + 256);
+                if (valid) tau = fmaxf(tau, ordered_to_float(*(volatile uint32_t *)tau_sh));
+                if (args.debug_mode != 1)
+                    filter_tile<GCAP>(tbase, tile0 + half * 128, special, ib_hi, self, L, lane,
+                                      args.debug_mode, tau_sh, tau, cnt, list, ctr);
+                ctr[3] += TC_BN / 32;
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_l[as]);
+                as ^= 1;
+                if (as == 0) acc_ph ^= 1;
+            }
+            if (valid) {
+                tau = fmaxf(tau, ordered_to_float(*(volatile uint32_t *)tau_sh));
+                args.cand_cnt[slot] = cnt;
+                args.cand_tau[slot] = tau;
+            }
+        }
+        if (lane == 0) {
+            PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
+            for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::cluster_sync_all();  // the peer may still be signalling this CTA's barriers / TMEM
+    if (warp == 2) ptx::tmem_dealloc_2sm<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------
@@ -520,7 +686,7 @@ struct RerankArgs {
     int q_begin;           // absolute query index of row 0 (self-join id, output naming)
     int out_q_begin;       // output row = q - out_q_begin
     int n_rows, nb, d, k, kcap, self_join;
-    int nsplit, gcap;
+    int nlists, gcap;  // candidate lists per row (base splits x column halves)
     const key64_t *cand;
     const int *cand_cnt;
     const float *cand_tau;
@@ -547,8 +713,8 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
     // gather the candidate ids of all splits; tau = max over splits
     int n = 0;
     float tau = __int_as_float(0xff800000);
-    for (int s = 0; s < a.nsplit; ++s) {
-        const size_t slot = (size_t)r * a.nsplit + s;
+    for (int s = 0; s < a.nlists; ++s) {
+        const size_t slot = (size_t)r * a.nlists + s;
         const int c = a.cand_cnt[slot];
         const key64_t *l = a.cand + slot * a.gcap;
         for (int i = lane; i < c; i += 32) keys[n + i] = __ldcg(l + i);
@@ -724,6 +890,11 @@ int pick_L(int kcap, bool inexact) {
 int pick_gcap(int L) { return L <= 32 ? 128 : (L <= 64 ? 256 : 512); }
 
 template <int GCAP>
+size_t tc2_smem_bytes(const TcPlan &p) {
+    return 1024 + (size_t)p.a_bytes / 2 + (size_t)TC2_NSTAGE * p.b_bytes +
+           sizeof(Tc2SmemTail<GCAP>);
+}
+template <int GCAP>
 size_t tc_smem_bytes(const TcPlan &p) {
     return 1024 + (size_t)p.a_bytes + (size_t)TC_NSTAGE * p.b_bytes + sizeof(TcSmemTail<GCAP>);
 }
@@ -731,9 +902,18 @@ size_t tc_smem_bytes(const TcPlan &p) {
 struct TcLayout {
     size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
     int d16, L, L_exact, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
+    int variant, halves, nlists;  // variant 2 = CTA-pair kernel (two column halves per row)
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// 3 = CTA-pair kernel with collector warps (knn_tc3.cu, default); PQH_TC_VARIANT=1 / 2 select
+// the earlier single-CTA / pair kernels of this file, kept for A/B measurements
+int tc_variant() {
+    const char *v = getenv("PQH_TC_VARIANT");
+    const int x = v ? atoi(v) : 3;
+    return (x == 1 || x == 2) ? x : 3;
+}
 
 void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join, int num_sms,
                TcLayout *lo) {
@@ -742,12 +922,20 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->L = pick_L(kcap, true);
     lo->L_exact = pick_L(kcap, false);
     lo->gcap = pick_gcap(lo->L);
-    lo->n_qtiles = (n_rows + TC_ROWS - 1) / TC_ROWS;
-    lo->n_btiles = (nb + TC_BN - 1) / TC_BN;
+    lo->variant = tc_variant();
+    lo->halves = lo->variant == 2 ? 2 : 1;
+    const int bn = lo->variant == 2 ? 256 : TC_BN;
+    const int units = lo->variant == 1 ? num_sms : num_sms / 2;
+    const int qrows = lo->variant == 3 ? 512 : TC_ROWS;  // query rows per work item
+    lo->n_qtiles = (n_rows + qrows - 1) / qrows;
+    lo->n_btiles = (nb + bn - 1) / bn;
     int nsplit = 1;
-    while (nsplit < 4 && lo->n_qtiles * nsplit < 2 * num_sms && lo->n_btiles / (nsplit * 2) >= 16)
+    const int max_lists = 2048 / lo->gcap;
+    while (nsplit * 2 * lo->halves <= max_lists && nsplit < 4 &&
+           lo->n_qtiles * nsplit < 2 * units && lo->n_btiles / (nsplit * 2) >= 8)
         nsplit *= 2;
     lo->nsplit = nsplit;
+    lo->nlists = nsplit * lo->halves;
     lo->tiles_per_split = (lo->n_btiles + nsplit - 1) / nsplit;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -762,9 +950,9 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->fold_a = take((size_t)TC_ROWS * FOLD_COLS * sizeof(__half));
     lo->norm_b = take((size_t)nb * sizeof(double));
     lo->norm_q = self_join ? lo->norm_b : take((size_t)nq_src_rows * sizeof(double));
-    lo->cand = take((size_t)n_rows * nsplit * lo->gcap * sizeof(key64_t));
-    lo->cnt = take((size_t)n_rows * nsplit * sizeof(int));
-    lo->tau = take((size_t)n_rows * nsplit * sizeof(float));
+    lo->cand = take((size_t)n_rows * lo->nlists * lo->gcap * sizeof(key64_t));
+    lo->cnt = take((size_t)n_rows * lo->nlists * sizeof(int));
+    lo->tau = take((size_t)n_rows * lo->nlists * sizeof(float));
     lo->fb_rows = take((size_t)n_rows * sizeof(int));
     lo->total = off + 1024;
 }
@@ -779,8 +967,15 @@ bool tc_supported(int n_rows, int nb, int d, int k, int self_join) {
     TcPlan p;
     if (!build_plan((d + 15) / 16 * 16, &p)) return false;
     const int gcap = pick_gcap(pick_L(kcap, true));
-    size_t smem = gcap == 128 ? tc_smem_bytes<128>(p)
-                              : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
+    size_t smem;
+    if (tc_variant() == 3)
+        return tc3_pick_nstage(&p) >= 2;
+    if (tc_variant() == 2)
+        smem = gcap == 128 ? tc2_smem_bytes<128>(p)
+                           : (gcap == 256 ? tc2_smem_bytes<256>(p) : tc2_smem_bytes<512>(p));
+    else
+        smem = gcap == 128 ? tc_smem_bytes<128>(p)
+                           : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
     return smem <= 227 * 1024;
 }
 
@@ -854,15 +1049,17 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     if (!build_plan(lo.d16, &args.plan)) return cudaErrorInvalidValue;
     const uint64_t a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
     const uint32_t boxc[3] = {64, 32, 16};
+    const uint32_t a_box_rows = lo.variant == 2 ? 128 : TC_ROWS;
+    const uint32_t b_box_rows = lo.variant == 3 ? 64 : TC_BN;
     for (int c = 0; c < 3; ++c) {
         // classes a small d never uses still need a legal box
         const uint32_t bc = boxc[c] <= (uint32_t)lo.d16 ? boxc[c] : 16;
-        if (!make_map(&maps.a[c], xh_q, a_rows, lo.d16, bc, TC_ROWS) ||
-            !make_map(&maps.b[c], xh_b, nb, lo.d16, bc, TC_BN))
+        if (!make_map(&maps.a[c], xh_q, a_rows, lo.d16, bc, a_box_rows) ||
+            !make_map(&maps.b[c], xh_b, nb, lo.d16, bc, b_box_rows))
             return cudaErrorInvalidValue;
     }
-    if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, TC_ROWS) ||
-        !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, TC_BN))
+    if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, a_box_rows) ||
+        !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, b_box_rows))
         return cudaErrorInvalidValue;
 
     args.n_rows = n_rows;
@@ -878,6 +1075,8 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         const char *dbg = getenv("PQH_TC_DEBUG");
         args.debug_mode = dbg ? atoi(dbg) : 0;
     }
+    args.nstage = 0;
+    args.kcap = kcap;
     args.L_exact = lo.L_exact;
     args.L_inexact = lo.L;
     args.sc = sc;
@@ -886,28 +1085,34 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     args.cand_tau = tau;
 
     const int n_items = lo.n_qtiles * lo.nsplit;
-    const int grid = n_items < num_sms ? n_items : num_sms;
     size_t smem;
     if (ev) cudaEventRecord(ev[1], stream);
-    if (lo.gcap == 128) {
-        smem = tc_smem_bytes<128>(args.plan);
-        if ((e = cudaFuncSetAttribute(knn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem)) != cudaSuccess)
+#define LAUNCH_TC(KERNEL, SMEM, GRID)                                                            \
+    do {                                                                                         \
+        smem = (SMEM);                                                                           \
+        if ((e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)smem)) != cudaSuccess)                                \
+            return e;                                                                            \
+        KERNEL<<<(GRID), TC_THREADS, smem, stream>>>(maps, args);                                \
+    } while (0)
+    if (lo.variant == 3) {
+        args.nstage = tc3_pick_nstage(&args.plan);
+        if (args.nstage < 2) return cudaErrorInvalidValue;
+        if ((e = launch_tc3(&maps, &args, lo.gcap, n_items, num_sms, stream)) != cudaSuccess)
             return e;
-        knn_tc_kernel<128><<<grid, TC_THREADS, smem, stream>>>(maps, args);
-    } else if (lo.gcap == 256) {
-        smem = tc_smem_bytes<256>(args.plan);
-        if ((e = cudaFuncSetAttribute(knn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem)) != cudaSuccess)
-            return e;
-        knn_tc_kernel<256><<<grid, TC_THREADS, smem, stream>>>(maps, args);
+    } else if (lo.variant == 2) {
+        const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
+        const int grid = 2 * clusters;
+        if (lo.gcap == 128) LAUNCH_TC(knn_tc2_kernel<128>, tc2_smem_bytes<128>(args.plan), grid);
+        else if (lo.gcap == 256) LAUNCH_TC(knn_tc2_kernel<256>, tc2_smem_bytes<256>(args.plan), grid);
+        else LAUNCH_TC(knn_tc2_kernel<512>, tc2_smem_bytes<512>(args.plan), grid);
     } else {
-        smem = tc_smem_bytes<512>(args.plan);
-        if ((e = cudaFuncSetAttribute(knn_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem)) != cudaSuccess)
-            return e;
-        knn_tc_kernel<512><<<grid, TC_THREADS, smem, stream>>>(maps, args);
+        const int grid = n_items < num_sms ? n_items : num_sms;
+        if (lo.gcap == 128) LAUNCH_TC(knn_tc_kernel<128>, tc_smem_bytes<128>(args.plan), grid);
+        else if (lo.gcap == 256) LAUNCH_TC(knn_tc_kernel<256>, tc_smem_bytes<256>(args.plan), grid);
+        else LAUNCH_TC(knn_tc_kernel<512>, tc_smem_bytes<512>(args.plan), grid);
     }
+#undef LAUNCH_TC
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (ev) cudaEventRecord(ev[2], stream);
@@ -925,7 +1130,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     ra.k = k;
     ra.kcap = kcap;
     ra.self_join = self_join;
-    ra.nsplit = lo.nsplit;
+    ra.nlists = lo.nlists;
     ra.gcap = lo.gcap;
     ra.cand = cand;
     ra.cand_cnt = cnt;
@@ -937,7 +1142,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     ra.dis = d_dis;
     ra.fb_rows = fb_rows;
     ra.fb_count = &sc->fb_count;
-    const int nmax = lo.gcap * lo.nsplit;
+    const int nmax = lo.gcap * lo.nlists;
     const int rgrid = (n_rows + RR_WARPS - 1) / RR_WARPS;
     const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
 #define LAUNCH_RR(N)                                                                             \
@@ -969,6 +1174,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         times->candidates = 0;
         for (int i = 0; i < 64; ++i) times->candidates += (double)hsc.cand_total[i];
         times->inexact = (int)hsc.inexact;
+        if (getenv("PQH_TC_DEBUG"))
+            fprintf(stderr, "tc dbg: slow_chunks=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu\n",
+                    hsc.dbg[0], hsc.dbg[1], hsc.dbg[2], hsc.dbg[3]);
         if (ev) {
             cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);
             cudaEventElapsedTime(&times->ms_gemm, ev[1], ev[2]);

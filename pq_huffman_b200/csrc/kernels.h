@@ -35,4 +35,8 @@ int tc3_pick_nstage(const void *plan);
 cudaError_t launch_tc3(const void *maps, const void *args, int gcap, int n_items, int num_sms,
                        cudaStream_t stream);
 
+// ---- knn_tcs.cu (streaming kernel for large d) ----
+cudaError_t launch_tcs(const void *maps, const void *args, int gcap, int d16, int n_items,
+                       int num_sms, cudaStream_t stream);
+
 }  // namespace pqh

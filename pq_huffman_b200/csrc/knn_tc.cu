@@ -125,125 +125,6 @@ struct TcSmemTail {
     uint32_t tmem_base;
 };
 
-// Predicated append of (ordered(-score), id) to a row's candidate list: no branch.
-__device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint32_t score_bits,
-                                          int id) {
-    const uint32_t u = score_bits ^ 0x80000000u;                          // bits of -score
-    const uint32_t hi = u ^ ((uint32_t)((int)u >> 31) | 0x80000000u);     // float_to_ordered
-    const key64_t key = ((key64_t)hi << 32) | (key64_t)(uint32_t)id;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred q;\n\t"
-        "setp.ne.b32 q, %0, 0;\n\t"
-        "@q st.global.cg.b64 [%1], %2;\n\t"
-        "}\n"
-        :
-        : "r"((int)p), "l"(list + cnt), "l"(key)
-        : "memory");
-    cnt += p ? 1 : 0;
-}
-
-// Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
-// it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
-// A thread keeps its row's running threshold tau and appends every score above it to the row's
-// candidate list; full lists are shrunk to the L best (shrink_row) and tau raised.
-// tau_shared (pair kernel): ordered bits of the threshold shared by the two threads that
-// filter the two column halves of the same row.
-template <int GCAP>
-__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
-                                            int self, int L, int lane, int debug_mode,
-                                            uint32_t *tau_shared, float &tau, int &cnt,
-                                            key64_t *list, unsigned (&ctr)[4]) {
-    const int trigger = GCAP - 32;  // hard limit; soft shrinks happen in idle time
-    const int id_lim = special ? ib_hi : 0x7fffffff;
-    // One chunk of 32 columns at a time, single register buffer, loop not unrolled: the other
-    // epilogue warp of the scheduler hides the TMEM latency, and the slow path exists once and
-    // scans the registers directly (no TMEM re-read, small code).
-#pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-        uint32_t cur[32];
-        ptx::tmem_ld_32x32b_x32(tbase + c * 32, cur);
-        ptx::tmem_wait_ld();
-        unsigned gmask = 0;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            const int o = q4 * 8;
-            float m = ptx::fmax3(__uint_as_float(cur[o]), __uint_as_float(cur[o + 1]),
-                                 __uint_as_float(cur[o + 2]));
-            m = ptx::fmax3(m, __uint_as_float(cur[o + 3]), __uint_as_float(cur[o + 4]));
-            m = ptx::fmax3(m, __uint_as_float(cur[o + 5]), __uint_as_float(cur[o + 6]));
-            m = fmaxf(m, __uint_as_float(cur[o + 7]));
-            gmask |= (m > tau) ? (1u << q4) : 0u;
-        }
-        // groups of 8 columns in which some row of this warp has a candidate
-        const unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
-        if (groups != 0 && debug_mode != 2) {
-            ++ctr[0];
-            const int col0 = col_base + c * 32;
-            // Branch-free scan of the flagged groups: divergent branches cost ~25 cycles each
-            // on this path, a predicated store costs one issue slot.
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                if (groups & (1u << q4)) {  // warp-uniform
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t u = cur[q4 * 8 + j];
-                        const int id = col0 + q4 * 8 + j;
-                        const bool p = (__uint_as_float(u) > tau) & (id < id_lim) & (id != self);
-                        append_if(p, list, cnt, u, id);
-                    }
-                }
-            }
-            unsigned need = __ballot_sync(0xffffffffu, cnt > trigger);
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                key64_t *l = reinterpret_cast<key64_t *>(
-                    __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
-                ++ctr[1];
-                if (lane == src) {
-                    cnt = L;
-                    tau = fmaxf(tau, -ordered_to_float(x));
-                    if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
-                }
-            }
-        }
-    }
-}
-
-// While the tensor cores have not finished the next accumulator tile, use the idle time to
-// shrink lists that have grown past 2L: the threshold then stays fresh without a shrink ever
-// standing between a finished accumulator stage and its release (mandatory shrinks at the hard
-// capacity GCAP-32 remain in filter_tile, but become rare).
-template <int GCAP>
-__device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
-                                                           int lane, uint32_t *tau_shared,
-                                                           float &tau, int &cnt, key64_t *list,
-                                                           unsigned (&ctr)[4]) {
-    const int soft = (2 * L < GCAP - 32) ? 2 * L : GCAP - 32;
-    while (!ptx::mbar_test_wait(bar, parity)) {
-        const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
-        if (need == 0) {
-            ptx::mbar_wait(bar, parity);
-            return;
-        }
-        const int src = __ffs(need) - 1;
-        key64_t *l = reinterpret_cast<key64_t *>(
-            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-        const int n = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t x = (GCAP > 128 && n <= 128) ? shrink_row<128>(l, n, L, lane)
-                                                    : shrink_row<GCAP>(l, n, L, lane);
-        ++ctr[2];
-        if (lane == src) {
-            cnt = L;
-            tau = fmaxf(tau, -ordered_to_float(x));
-            if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
-        }
-    }
-}
-
 template <int GCAP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
@@ -334,6 +215,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(128, TC_BN);
             int stage = 0, as = 0;
             uint32_t ph = 0, acc_ph = 0, a_ph = 0;
+            long long mma_wait_b = 0, mma_wait_acc = 0;
+            const long long mma_t0 = clock64();
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int sp = item % args.nsplit;
                 int t_lo = sp * args.tiles_per_split;
@@ -342,8 +225,13 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 ptx::mbar_wait(&tail.a_full, a_ph);
                 a_ph ^= 1;
                 for (int t = t_lo; t < t_hi; ++t) {
+                    const long long m0 = clock64();
                     ptx::mbar_wait(&tail.b_full[stage], ph);
+                    const long long m1 = clock64();
                     ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
+                    const long long m2 = clock64();
+                    mma_wait_b += m1 - m0;
+                    mma_wait_acc += m2 - m1;
                     ptx::tc_fence_after_sync();
                     const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
                     const uint32_t a_base = ptx::smem_u32(smA);
@@ -375,6 +263,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 }
                 ptx::umma_commit(&tail.a_empty);
             }
+            PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
+            atomicAdd(&scw->dbg[6], (unsigned long long)mma_wait_b);
+            atomicAdd(&scw->dbg[7], (unsigned long long)mma_wait_acc);
+            atomicAdd(&scw->cand_total[63], (unsigned long long)(clock64() - mma_t0));
         }
     } else {
         // ===================== epilogue: threshold filter =====================
@@ -387,6 +279,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         int as = 0;
         uint32_t acc_ph = 0;
         unsigned ctr[4] = {0, 0, 0, 0};
+        long long t_wait = 0, t_work = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int qt = item / args.nsplit, sp = item % args.nsplit;
@@ -405,21 +298,29 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             const int ib_hi = (int)b_hi;
 
             for (int t = t_lo; t < t_hi; ++t) {
+                const long long tw0 = clock64();
                 wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
                                                  cnt, list, ctr);
+                const long long tw1 = clock64();
+                t_wait += tw1 - tw0;
                 ptx::tc_fence_after_sync();
                 const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
                 // id checks are only needed in the tile holding this row's own column and in
                 // the (possibly ragged) last tile
                 const int tile0 = t * TC_BN;
                 const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
+                auto release = [&]() {
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
+                };
                 if (args.debug_mode != 1)
                     filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
-                                      args.debug_mode, nullptr, tau, cnt, list, ctr);
+                                      args.debug_mode, nullptr, tau, cnt, list, ctr, release);
+                else
+                    release();
                 ctr[3] += TC_BN / 32;
-                ptx::tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
+                t_work += clock64() - tw1;
                 as ^= 1;
                 if (as == 0) acc_ph ^= 1;
             }
@@ -431,6 +332,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         if (lane == 0) {
             PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
             for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
+            atomicAdd(&scw->dbg[4], (unsigned long long)t_wait);
+            atomicAdd(&scw->dbg[5], (unsigned long long)t_work);
         }
     }
 
@@ -647,13 +550,17 @@ knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 const int tile0 = t * 256;
                 const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + 256);
                 if (valid) tau = fmaxf(tau, ordered_to_float(*(volatile uint32_t *)tau_sh));
+                auto release = [&]() {
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_l[as]);
+                };
                 if (args.debug_mode != 1)
                     filter_tile<GCAP>(tbase, tile0 + half * 128, special, ib_hi, self, L, lane,
-                                      args.debug_mode, tau_sh, tau, cnt, list, ctr);
+                                      args.debug_mode, tau_sh, tau, cnt, list, ctr, release);
+                else
+                    release();
                 ctr[3] += TC_BN / 32;
-                ptx::tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_l[as]);
                 as ^= 1;
                 if (as == 0) acc_ph ^= 1;
             }
@@ -797,7 +704,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         }
     }
     if (lane == 0) {
-        atomicAdd(const_cast<unsigned long long *>(&a.sc->cand_total[blockIdx.x & 63]),
+        atomicAdd(const_cast<unsigned long long *>(&a.sc->cand_total[blockIdx.x & 31]),
                   (unsigned long long)n);
         if (!ok) {
             const uint32_t p = atomicAdd(a.fb_count, 1u);
@@ -882,7 +789,14 @@ bool build_plan(int d16, TcPlan *p) {
 // candidates kept per row: 4x the neighbours asked for when the FP16 operands are rounded
 // (slack for the certificate), 2x when they are exact (integer-valued data)
 int pick_L(int kcap, bool inexact) {
-    int L = (inexact ? 4 : 2) * kcap;
+    if (!inexact) {
+        // exact operands: the certificate only has to absorb the accumulation bound, a
+        // margin of half the neighbours is plenty; a short list keeps the threshold tight
+        const char *e = getenv("PQH_TC_LEXACT");
+        if (e) return atoi(e);
+        return (kcap + kcap / 2 + 7) / 8 * 8;
+    }
+    int L = 4 * kcap;
     L = (L + 31) / 32 * 32;
     if (L < 32) L = 32;
     return L;
@@ -907,12 +821,35 @@ struct TcLayout {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// 3 = CTA-pair kernel with collector warps (knn_tc3.cu, default); PQH_TC_VARIANT=1 / 2 select
-// the earlier single-CTA / pair kernels of this file, kept for A/B measurements
+// Kernel variants.  1 = single-CTA kernel with the query tile resident in shared memory
+// (knn_tc_kernel; default whenever the tile fits, d <= ~144); 4 = streaming kernel for larger d
+// (knn_tcs.cu).  PQH_TC_VARIANT=2 / 3 select the CTA-pair experiments (this file / knn_tc3.cu),
+// kept for A/B measurements -- see profiles/README.md for why they are not the default.
 int tc_variant() {
     const char *v = getenv("PQH_TC_VARIANT");
-    const int x = v ? atoi(v) : 3;
-    return (x == 1 || x == 2) ? x : 3;
+    const int x = v ? atoi(v) : 1;
+    return (x >= 1 && x <= 4) ? x : 1;
+}
+
+// does the resident-A plan of `variant` fit in shared memory for this d16 / list capacity?
+bool resident_fits(int variant, int d16, int gcap) {
+    TcPlan p;
+    if (!build_plan(d16, &p)) return false;
+    if (variant == 3) return tc3_pick_nstage(&p) >= 2;
+    size_t smem;
+    if (variant == 2)
+        smem = gcap == 128 ? tc2_smem_bytes<128>(p)
+                           : (gcap == 256 ? tc2_smem_bytes<256>(p) : tc2_smem_bytes<512>(p));
+    else
+        smem = gcap == 128 ? tc_smem_bytes<128>(p)
+                           : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
+    return smem <= 227 * 1024;
+}
+
+int tc_pick_variant(int d16, int gcap) {
+    int v = tc_variant();
+    if (v != 4 && !resident_fits(v, d16, gcap)) v = 4;
+    return v;
 }
 
 void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join, int num_sms,
@@ -922,7 +859,7 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->L = pick_L(kcap, true);
     lo->L_exact = pick_L(kcap, false);
     lo->gcap = pick_gcap(lo->L);
-    lo->variant = tc_variant();
+    lo->variant = tc_pick_variant(lo->d16, lo->gcap);
     lo->halves = lo->variant == 2 ? 2 : 1;
     const int bn = lo->variant == 2 ? 256 : TC_BN;
     const int units = lo->variant == 1 ? num_sms : num_sms / 2;
@@ -964,19 +901,7 @@ bool tc_supported(int n_rows, int nb, int d, int k, int self_join) {
     if (kcap < 1 || kcap > 32) return false;
     if (nb < 2048 || n_rows < 1) return false;
     if (d < 1 || d > 4096) return false;
-    TcPlan p;
-    if (!build_plan((d + 15) / 16 * 16, &p)) return false;
-    const int gcap = pick_gcap(pick_L(kcap, true));
-    size_t smem;
-    if (tc_variant() == 3)
-        return tc3_pick_nstage(&p) >= 2;
-    if (tc_variant() == 2)
-        smem = gcap == 128 ? tc2_smem_bytes<128>(p)
-                           : (gcap == 256 ? tc2_smem_bytes<256>(p) : tc2_smem_bytes<512>(p));
-    else
-        smem = gcap == 128 ? tc_smem_bytes<128>(p)
-                           : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
-    return smem <= 227 * 1024;
+    return true;  // the streaming kernel takes every d the resident kernels cannot
 }
 
 size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms) {
@@ -1046,7 +971,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     // ---- tensor maps + plan ----
     TcMaps maps;
     TcArgs args;
-    if (!build_plan(lo.d16, &args.plan)) return cudaErrorInvalidValue;
+    if (!build_plan(lo.d16, &args.plan) && lo.variant != 4) return cudaErrorInvalidValue;
     const uint64_t a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
     const uint32_t boxc[3] = {64, 32, 16};
     const uint32_t a_box_rows = lo.variant == 2 ? 128 : TC_ROWS;
@@ -1095,7 +1020,10 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             return e;                                                                            \
         KERNEL<<<(GRID), TC_THREADS, smem, stream>>>(maps, args);                                \
     } while (0)
-    if (lo.variant == 3) {
+    if (lo.variant == 4) {
+        if ((e = launch_tcs(&maps, &args, lo.gcap, lo.d16, n_items, num_sms, stream)) != cudaSuccess)
+            return e;
+    } else if (lo.variant == 3) {
         args.nstage = tc3_pick_nstage(&args.plan);
         if (args.nstage < 2) return cudaErrorInvalidValue;
         if ((e = launch_tc3(&maps, &args, lo.gcap, n_items, num_sms, stream)) != cudaSuccess)
@@ -1172,11 +1100,16 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     *h_fb_count = hsc.fb_count;
     if (times) {
         times->candidates = 0;
-        for (int i = 0; i < 64; ++i) times->candidates += (double)hsc.cand_total[i];
+        for (int i = 0; i < 32; ++i) times->candidates += (double)hsc.cand_total[i];
         times->inexact = (int)hsc.inexact;
         if (getenv("PQH_TC_DEBUG"))
-            fprintf(stderr, "tc dbg: slow_chunks=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu\n",
-                    hsc.dbg[0], hsc.dbg[1], hsc.dbg[2], hsc.dbg[3]);
+            fprintf(stderr,
+                    "tc dbg: slow_chunks=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu | "
+                    "epi warps: wait %.3g work %.3g cyc | mma thread: wait_b %.3g wait_acc %.3g "
+                    "total %.3g cyc (sums over CTAs)\n",
+                    hsc.dbg[0], hsc.dbg[1], hsc.dbg[2], hsc.dbg[3], (double)hsc.dbg[4],
+                    (double)hsc.dbg[5], (double)hsc.dbg[6], (double)hsc.dbg[7],
+                    (double)hsc.cand_total[63]);
         if (ev) {
             cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);
             cudaEventElapsedTime(&times->ms_gemm, ev[1], ev[2]);

@@ -136,5 +136,130 @@ __device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lan
 }
 
 
+// Predicated append of (ordered(-score), id) to a row's candidate list: no branch.
+__device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint32_t score_bits,
+                                          int id) {
+    const uint32_t u = score_bits ^ 0x80000000u;                          // bits of -score
+    const uint32_t hi = u ^ ((uint32_t)((int)u >> 31) | 0x80000000u);     // float_to_ordered
+    const key64_t key = ((key64_t)hi << 32) | (key64_t)(uint32_t)id;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "@q st.global.b64 [%1], %2;\n\t"
+        "}\n"
+        :
+        : "r"((int)p), "l"(list + cnt), "l"(key)
+        : "memory");
+    cnt += p ? 1 : 0;
+}
+
+// Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
+// it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
+// The whole 32 x 128 slice is first copied to registers (two 64-column tcgen05.ld in flight
+// together) and the accumulator stage is released to the tensor cores IMMEDIATELY
+// (`release`): everything whose duration varies -- scanning hit groups, appending, shrinking --
+// then works from registers and never delays the next MMA.
+// A thread keeps its row's running threshold tau and appends every score above it to the row's
+// candidate list; full lists are shrunk to the L best (shrink_row) and tau raised.
+// tau_shared (pair kernel): ordered bits of the threshold shared by the two threads that
+// filter the two column halves of the same row.
+template <int GCAP, class Release>
+__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
+                                            int self, int L, int lane, int debug_mode,
+                                            uint32_t *tau_shared, float &tau, int &cnt,
+                                            key64_t *list, unsigned (&ctr)[4], Release release) {
+    const int trigger = GCAP - 32;  // hard limit; soft shrinks happen in idle time
+    const int id_lim = special ? ib_hi : 0x7fffffff;
+    uint32_t ra[64], rb[64];
+    ptx::tmem_ld_32x32b_x64(tbase, ra);
+    ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+    ptx::tmem_wait_ld();
+    release();
+#pragma unroll
+    for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t(&buf)[64] = (c < 2) ? ra : rb;
+        const int o32 = (c & 1) * 32;
+        unsigned gmask = 0;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int o = o32 + q4 * 8;
+            float m = ptx::fmax3(__uint_as_float(buf[o]), __uint_as_float(buf[o + 1]),
+                                 __uint_as_float(buf[o + 2]));
+            m = ptx::fmax3(m, __uint_as_float(buf[o + 3]), __uint_as_float(buf[o + 4]));
+            m = ptx::fmax3(m, __uint_as_float(buf[o + 5]), __uint_as_float(buf[o + 6]));
+            m = fmaxf(m, __uint_as_float(buf[o + 7]));
+            gmask |= (m > tau) ? (1u << q4) : 0u;
+        }
+        // groups of 8 columns in which some row of this warp has a candidate
+        const unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
+        if (groups != 0 && debug_mode != 2) {
+            ++ctr[0];
+            const int col0 = col_base + c * 32;
+            // Branch-free scan of the flagged groups: divergent branches cost ~25 cycles each
+            // on this path, a predicated store costs one issue slot.
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                if (groups & (1u << q4)) {  // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t u = buf[o32 + q4 * 8 + j];
+                        const int id = col0 + q4 * 8 + j;
+                        const bool p = (__uint_as_float(u) > tau) & (id < id_lim) & (id != self);
+                        append_if(p, list, cnt, u, id);
+                    }
+                }
+            }
+            unsigned need = __ballot_sync(0xffffffffu, cnt > trigger);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                key64_t *l = reinterpret_cast<key64_t *>(
+                    __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+                const int n = __shfl_sync(0xffffffffu, cnt, src);
+                const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
+                ++ctr[1];
+                if (lane == src) {
+                    cnt = L;
+                    tau = fmaxf(tau, -ordered_to_float(x));
+                    if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
+                }
+            }
+        }
+    }
+}
+
+// While the tensor cores have not finished the next accumulator tile, use the idle time to
+// shrink lists that have grown past 2L: the threshold then stays fresh without a shrink ever
+// standing between a finished accumulator stage and its release (mandatory shrinks at the hard
+// capacity GCAP-32 remain in filter_tile, but become rare).
+template <int GCAP>
+__device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
+                                                           int lane, uint32_t *tau_shared,
+                                                           float &tau, int &cnt, key64_t *list,
+                                                           unsigned (&ctr)[4]) {
+    const int soft = (L + L / 2 < GCAP - 32) ? L + L / 2 : GCAP - 32;
+    while (!ptx::mbar_test_wait(bar, parity)) {
+        const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
+        if (need == 0) {
+            ptx::mbar_wait(bar, parity);
+            return;
+        }
+        const int src = __ffs(need) - 1;
+        key64_t *l = reinterpret_cast<key64_t *>(
+            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+        const int n = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t x = (GCAP > 128 && n <= 128) ? shrink_row<128>(l, n, L, lane)
+                                                    : shrink_row<GCAP>(l, n, L, lane);
+        ++ctr[2];
+        if (lane == src) {
+            cnt = L;
+            tau = fmaxf(tau, -ordered_to_float(x));
+            if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
+        }
+    }
+}
+
+
 }  // namespace
 }  // namespace pqh

@@ -1,0 +1,271 @@
+// knn_tcs.cu -- the "streaming" distance-GEMM + filter kernel for dimensions whose query tile
+// does not fit in shared memory (GIST-shaped d = 960, anything above ~144).
+//
+// Same geometry and epilogue as knn_tc_kernel (256 query rows per CTA as two M=128 accumulator
+// tiles, base tiles of 128 rows, two accumulator stages, eight filter warps), but BOTH operands
+// are streamed through one ring of K-blocks: a stage holds the [256 x 64] slice of the query
+// tile and the [128 x 64] slice of the base tile for one K-block (48 KB), the MMA thread
+// accumulates over all K-blocks of a tile before committing the accumulator.  With d this large
+// the kernel is bound by the tensor cores and by L2->SM operand traffic, not by the epilogue:
+// each accumulator element is the result of d/128 times more MMA work than at SIFT's d = 128.
+#include <cstdlib>
+
+#include "kernels.h"
+#include "knn_tc_common.cuh"
+
+namespace pqh {
+
+namespace {
+
+constexpr int TS_NSTAGE = 4;
+constexpr int TS_A_BYTES = TC_ROWS * 128;  // one K-block of the query tile (SW128: 64 halves)
+constexpr int TS_B_BYTES = TC_BN * 128;
+constexpr int TS_STAGE_BYTES = TS_A_BYTES + TS_B_BYTES;
+
+struct TsSmemTail {
+    uint64_t full[TS_NSTAGE], empty[TS_NSTAGE];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+// K-blocks of a padded operand row of d16 halves followed by the 16 fold columns:
+// full 64-half blocks (SW128), then an optional 32-half (SW64) and 16-half (SW32) block, then
+// the fold block (SW32, separate tensors).
+struct KBlocks {
+    int nfull, has32, has16, total;
+    __device__ __host__ explicit KBlocks(int d16) {
+        nfull = d16 / 64;
+        const int rem = d16 - nfull * 64;
+        has32 = rem >= 32;
+        has16 = (rem - (has32 ? 32 : 0)) >= 16;
+        total = nfull + has32 + has16 + 1;
+    }
+    // -> bytes per row of block i, element offset, fold flag
+    __device__ __forceinline__ void get(int i, int &bytes, int &k_off, int &fold) const {
+        fold = 0;
+        if (i < nfull) {
+            bytes = 128;
+            k_off = i * 64;
+            return;
+        }
+        int j = i - nfull;
+        if (has32) {
+            if (j == 0) {
+                bytes = 64;
+                k_off = nfull * 64;
+                return;
+            }
+            --j;
+        }
+        if (has16) {
+            if (j == 0) {
+                bytes = 32;
+                k_off = nfull * 64 + (has32 ? 32 : 0);
+                return;
+            }
+            --j;
+        }
+        bytes = 32;
+        k_off = 0;
+        fold = 1;
+    }
+};
+
+template <int GCAP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    TsSmemTail &tail = *reinterpret_cast<TsSmemTail *>(smem + TS_NSTAGE * TS_STAGE_BYTES);
+    const KBlocks kb(d16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 3; ++i) {
+            ptx::prefetch_tmap(&maps.a[i]);
+            ptx::prefetch_tmap(&maps.b[i]);
+        }
+        ptx::prefetch_tmap(&maps.fa);
+        ptx::prefetch_tmap(&maps.fb);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < TS_NSTAGE; ++i) {
+            ptx::mbar_init(&tail.full[i], 1);
+            ptx::mbar_init(&tail.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tail.acc_full[i], 1);
+            ptx::mbar_init(&tail.acc_empty[i], TC_EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<512>(&tail.tmem_base);
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = tail.tmem_base;
+
+    const int n_items = args.n_qtiles * args.nsplit;
+
+    if (warp == 0) {
+        // ===================== TMA producer: one K-block of A and B per stage =============
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int qt = item / args.nsplit, sp = item % args.nsplit;
+                int t_lo = sp * args.tiles_per_split;
+                int t_hi = t_lo + args.tiles_per_split;
+                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                const int arow = args.q_op_begin + qt * TC_ROWS;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    for (int i = 0; i < kb.total; ++i) {
+                        int bytes, k_off, fold;
+                        kb.get(i, bytes, k_off, fold);
+                        ptx::mbar_wait(&tail.empty[stage], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&tail.full[stage], (TC_ROWS + TC_BN) * bytes);
+                        uint8_t *sa = smem + stage * TS_STAGE_BYTES;
+                        uint8_t *sb = sa + TS_A_BYTES;
+                        if (fold) {
+                            ptx::tma_load_2d(sa, &maps.fa, &tail.full[stage], 0, 0);
+                            ptx::tma_load_2d(sb, &maps.fb, &tail.full[stage], 0, t * TC_BN);
+                        } else {
+                            const int cls = seg_class(bytes);
+                            ptx::tma_load_2d(sa, &maps.a[cls], &tail.full[stage], k_off, arow);
+                            ptx::tma_load_2d(sb, &maps.b[cls], &tail.full[stage], k_off, t * TC_BN);
+                        }
+                        if (++stage == TS_NSTAGE) {
+                            stage = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(128, TC_BN);
+            int stage = 0, as = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int sp = item % args.nsplit;
+                int t_lo = sp * args.tiles_per_split;
+                int t_hi = t_lo + args.tiles_per_split;
+                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
+                    ptx::tc_fence_after_sync();
+                    for (int i = 0; i < kb.total; ++i) {
+                        int bytes, k_off, fold;
+                        kb.get(i, bytes, k_off, fold);
+                        ptx::mbar_wait(&tail.full[stage], ph);
+                        ptx::tc_fence_after_sync();
+                        const uint32_t a_base = ptx::smem_u32(smem + stage * TS_STAGE_BYTES);
+                        const uint32_t b_base = a_base + TS_A_BYTES;
+                        const uint32_t sbo = 8 * bytes, lay = seg_layout(bytes);
+#pragma unroll 1
+                        for (int g = 0; g < 2; ++g) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + g * 128);
+                            const uint32_t a_addr = a_base + g * 128 * bytes;
+                            for (int kk = 0; kk < bytes / 32; ++kk)
+                                ptx::umma_f16(d_tmem,
+                                              ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
+                                              ptx::make_smem_desc(b_base + kk * 32, sbo, lay), idesc,
+                                              (i > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&tail.empty[stage]);
+                        if (++stage == TS_NSTAGE) {
+                            stage = 0;
+                            ph ^= 1;
+                        }
+                    }
+                    ptx::umma_commit(&tail.acc_full[as]);
+                    as ^= 1;
+                    if (as == 0) acc_ph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: threshold filter (as knn_tc_kernel) =================
+        const int e = warp - 2;
+        const int g = e >> 2;
+        const int quad = warp & 3;
+        const int row_in_cta = g * 128 + quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
+        int as = 0;
+        uint32_t acc_ph = 0;
+        unsigned ctr[4] = {0, 0, 0, 0};
+        const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int qt = item / args.nsplit, sp = item % args.nsplit;
+            int t_lo = sp * args.tiles_per_split;
+            int t_hi = t_lo + args.tiles_per_split;
+            if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+            const int r = qt * TC_ROWS + row_in_cta;
+            const bool valid = r < args.n_rows;
+            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
+            key64_t *list = args.cand + slot * GCAP;
+            float tau = valid ? NEG_INF : POS_INF;
+            int cnt = 0;
+            long long b_hi = (long long)t_hi * TC_BN;
+            if (b_hi > args.nb) b_hi = args.nb;
+            const int ib_hi = (int)b_hi;
+            for (int t = t_lo; t < t_hi; ++t) {
+                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
+                                                 cnt, list, ctr);
+                ptx::tc_fence_after_sync();
+                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
+                const int tile0 = t * TC_BN;
+                const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
+                auto release = [&]() {
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
+                };
+                filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane, args.debug_mode,
+                                  nullptr, tau, cnt, list, ctr, release);
+                as ^= 1;
+                if (as == 0) acc_ph ^= 1;
+            }
+            if (valid) {
+                args.cand_cnt[slot] = cnt;
+                args.cand_tau[slot] = tau;
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+cudaError_t launch_tcs(const void *maps_v, const void *args_v, int gcap, int d16, int n_items,
+                       int num_sms, cudaStream_t stream) {
+    const TcMaps &maps = *static_cast<const TcMaps *>(maps_v);
+    const TcArgs &args = *static_cast<const TcArgs *>(args_v);
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    const size_t smem = 1024 + (size_t)TS_NSTAGE * TS_STAGE_BYTES + sizeof(TsSmemTail);
+    cudaError_t e;
+#define LAUNCH_TS(G)                                                                             \
+    do {                                                                                         \
+        if ((e = cudaFuncSetAttribute(knn_tcs_kernel<G>,                                         \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != \
+            cudaSuccess)                                                                         \
+            return e;                                                                            \
+        knn_tcs_kernel<G><<<grid, TC_THREADS, smem, stream>>>(maps, args, d16);                  \
+    } while (0)
+    if (gcap == 128) LAUNCH_TS(128);
+    else if (gcap == 256) LAUNCH_TS(256);
+    else LAUNCH_TS(512);
+#undef LAUNCH_TS
+    return cudaGetLastError();
+}
+
+}  // namespace pqh

@@ -10,7 +10,9 @@ from tests import oracle_ffi  # noqa: E402
 
 orc = oracle_ffi.Oracle()
 cases = [("sift", 5000, 128, 17), ("sift", 20000, 128, 17), ("deep", 8000, 96, 33),
-         ("uniform", 4096, 16, 9), ("gist", 3000, 144, 17), ("sift", 3000, 100, 5)]
+         ("uniform", 4096, 16, 9), ("gist", 3000, 144, 17), ("sift", 3000, 100, 5),
+         ("gist", 3000, 960, 17), ("gist", 5000, 200, 9), ("uniform", 4000, 272, 17),
+         ("deep", 20000, 96, 33)]
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 gens = {"sift": synth.sift_like, "gist": synth.gist_like, "deep": synth.deep_like,

@@ -123,6 +123,8 @@ struct TcSmemTail {
     uint64_t b_full[TC_NSTAGE], b_empty[TC_NSTAGE];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
+    int item_t0[2];  // first base tile of the current / next work item (set by the producer)
+    uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
 };
 
 template <int GCAP>
@@ -158,6 +160,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             ptx::mbar_init(&tail.acc_full[i], 1);
             ptx::mbar_init(&tail.acc_empty[i], TC_EPI_WARPS);
         }
+        ptx::mbar_init(&tail.t0_ready, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<512>(&tail.tmem_base);
@@ -171,7 +174,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (ptx::elect_one()) {
-            int stage = 0;
+            int stage = 0, it_par = 0, my_next = 0;
             uint32_t ph = 0, a_ph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int qt = item / args.nsplit, sp = item % args.nsplit;
@@ -179,6 +182,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 int t_hi = t_lo + args.tiles_per_split;
                 if (t_hi > args.n_btiles) t_hi = args.n_btiles;
                 ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
+                const int t0 = item_start_tile(args.sc, t_lo, t_hi, my_next);
+                my_next = t0;  // a full sweep ends where it started
+                tail.item_t0[it_par] = t0;
+                ptx::mbar_arrive(&tail.t0_ready);
                 ptx::mbar_arrive_expect_tx(&tail.a_full, plan.a_bytes);
                 for (int s = 0; s < plan.nseg; ++s) {
                     const TcSeg &sg = plan.seg[s];
@@ -189,7 +196,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                                          &tail.a_full, sg.k_off, args.q_op_begin + qt * TC_ROWS);
                 }
                 a_ph ^= 1;
-                for (int t = t_lo; t < t_hi; ++t) {
+                it_par ^= 1;
+                for (int i = 0; i < t_hi - t_lo; ++i) {
+                    const int t = item_tile(i, t0, t_lo, t_hi);
+                    if ((i & 7) == 0) publish_cursor(args.sc, t);
                     ptx::mbar_wait(&tail.b_empty[stage], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&tail.b_full[stage], plan.b_bytes);
                     uint8_t *dst = smB + stage * plan.b_bytes;
@@ -224,7 +234,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 if (t_hi > args.n_btiles) t_hi = args.n_btiles;
                 ptx::mbar_wait(&tail.a_full, a_ph);
                 a_ph ^= 1;
-                for (int t = t_lo; t < t_hi; ++t) {
+                for (int i = 0; i < t_hi - t_lo; ++i) {
                     const long long m0 = clock64();
                     ptx::mbar_wait(&tail.b_full[stage], ph);
                     const long long m1 = clock64();
@@ -280,6 +290,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         uint32_t acc_ph = 0;
         unsigned ctr[4] = {0, 0, 0, 0};
         long long t_wait = 0, t_work = 0;
+        int it_par = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int qt = item / args.nsplit, sp = item % args.nsplit;
@@ -297,13 +308,19 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             if (b_hi > args.nb) b_hi = args.nb;
             const int ib_hi = (int)b_hi;
 
-            for (int t = t_lo; t < t_hi; ++t) {
+            int t0 = 0;
+            for (int i = 0; i < t_hi - t_lo; ++i) {
                 const long long tw0 = clock64();
                 wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
                                                  cnt, list, ctr);
                 const long long tw1 = clock64();
                 t_wait += tw1 - tw0;
                 ptx::tc_fence_after_sync();
+                if (i == 0) {
+                    ptx::mbar_wait(&tail.t0_ready, (uint32_t)it_par);
+                    t0 = *reinterpret_cast<volatile int *>(&tail.item_t0[it_par]);
+                }
+                const int t = item_tile(i, t0, t_lo, t_hi);
                 const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
                 // id checks are only needed in the tile holding this row's own column and in
                 // the (possibly ragged) last tile
@@ -324,6 +341,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 as ^= 1;
                 if (as == 0) acc_ph ^= 1;
             }
+            it_par ^= 1;
             if (valid) {
                 args.cand_cnt[slot] = cnt;
                 args.cand_tau[slot] = tau;

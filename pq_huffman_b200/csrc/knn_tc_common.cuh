@@ -37,7 +37,8 @@ struct PrepScalars {
     uint32_t ymax_bits;    // max scaled base norm |y'| (float bits, rounded up)
     uint32_t inexact;      // some fp16(sigma*x) != sigma*x
     uint32_t fb_count;     // rows that failed the certificate
-    uint32_t pad[4];
+    uint32_t tile_cursor;  // base tile most recently started by some CTA (L2-friendly order)
+    uint32_t pad[3];
     unsigned long long cand_total[64];
     unsigned long long dbg[8];  // epilogue event counters: slow chunks, appends, hard/idle shrinks, chunks  // candidates re-ranked (spread to avoid contention)
 };
@@ -66,6 +67,29 @@ struct TcMaps {
     CUtensorMap fa;    // fold constants [256 x 16]
     CUtensorMap fb;    // fold pieces    [nb x 16]
 };
+
+// Base-tile order of one work item.  Every CTA sweeps ALL tiles of its range, so the order is
+// free: CTA 0 never restarts -- it keeps cycling through the tiles and publishes its position --
+// and every other CTA starts a new item at CTA 0's current tile and wraps around.  All CTAs then
+// stream the same window of the base operand at any moment, and a tile is fetched from HBM once
+// per sweep of the pack instead of once per CTA.  (Single writer: a cursor written by every CTA
+// never converges.)
+__device__ __forceinline__ int item_start_tile(const PrepScalars *sc, int t_lo, int t_hi,
+                                               int my_next) {
+    int c = my_next;
+    if (blockIdx.x != 0)
+        c = (int)*reinterpret_cast<const volatile uint32_t *>(&sc->tile_cursor);
+    return (c >= t_lo && c < t_hi) ? c : t_lo;
+}
+__device__ __forceinline__ int item_tile(int i, int t0, int t_lo, int t_hi) {
+    int t = t0 + i;
+    return t >= t_hi ? t - (t_hi - t_lo) : t;
+}
+__device__ __forceinline__ void publish_cursor(const PrepScalars *sc, int t) {
+    if (blockIdx.x == 0)
+        *reinterpret_cast<volatile uint32_t *>(&const_cast<PrepScalars *>(sc)->tile_cursor) =
+            (uint32_t)t;
+}
 
 __device__ __forceinline__ int seg_class(int bytes) { return bytes == 128 ? 0 : (bytes == 64 ? 1 : 2); }
 __device__ __forceinline__ uint32_t seg_layout(int bytes) {

@@ -26,6 +26,8 @@ struct TsSmemTail {
     uint64_t full[TS_NSTAGE], empty[TS_NSTAGE];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
+    int item_t0[2];
+    uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
 };
 
 // K-blocks of a padded operand row of d16 halves followed by the 16 fold columns:
@@ -99,6 +101,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
             ptx::mbar_init(&tail.acc_full[i], 1);
             ptx::mbar_init(&tail.acc_empty[i], TC_EPI_WARPS);
         }
+        ptx::mbar_init(&tail.t0_ready, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<512>(&tail.tmem_base);
@@ -112,7 +115,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
     if (warp == 0) {
         // ===================== TMA producer: one K-block of A and B per stage =============
         if (ptx::elect_one()) {
-            int stage = 0;
+            int stage = 0, it_par = 0, my_next = 0;
             uint32_t ph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int qt = item / args.nsplit, sp = item % args.nsplit;
@@ -120,7 +123,16 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 int t_hi = t_lo + args.tiles_per_split;
                 if (t_hi > args.n_btiles) t_hi = args.n_btiles;
                 const int arow = args.q_op_begin + qt * TC_ROWS;
-                for (int t = t_lo; t < t_hi; ++t) {
+                // the slot of item i is reused by item i+2; the producer is at most one ring
+                // (a fraction of a tile) ahead of the MMA, the epilogue at most two tiles behind
+                const int t0 = item_start_tile(args.sc, t_lo, t_hi, my_next);
+                my_next = t0;
+                tail.item_t0[it_par] = t0;
+                ptx::mbar_arrive(&tail.t0_ready);
+                it_par ^= 1;
+                for (int ti = 0; ti < t_hi - t_lo; ++ti) {
+                    const int t = item_tile(ti, t0, t_lo, t_hi);
+                    publish_cursor(args.sc, t);
                     for (int i = 0; i < kb.total; ++i) {
                         int bytes, k_off, fold;
                         kb.get(i, bytes, k_off, fold);
@@ -155,7 +167,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 int t_lo = sp * args.tiles_per_split;
                 int t_hi = t_lo + args.tiles_per_split;
                 if (t_hi > args.n_btiles) t_hi = args.n_btiles;
-                for (int t = t_lo; t < t_hi; ++t) {
+                for (int ti = 0; ti < t_hi - t_lo; ++ti) {
                     ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
                     ptx::tc_fence_after_sync();
                     for (int i = 0; i < kb.total; ++i) {
@@ -199,6 +211,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
         int as = 0;
         uint32_t acc_ph = 0;
         unsigned ctr[4] = {0, 0, 0, 0};
+        int it_par = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int qt = item / args.nsplit, sp = item % args.nsplit;
@@ -215,10 +228,16 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
             long long b_hi = (long long)t_hi * TC_BN;
             if (b_hi > args.nb) b_hi = args.nb;
             const int ib_hi = (int)b_hi;
-            for (int t = t_lo; t < t_hi; ++t) {
+            int t0 = 0;
+            for (int ti = 0; ti < t_hi - t_lo; ++ti) {
                 wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
                                                  cnt, list, ctr);
                 ptx::tc_fence_after_sync();
+                if (ti == 0) {
+                    ptx::mbar_wait(&tail.t0_ready, (uint32_t)it_par);
+                    t0 = *reinterpret_cast<volatile int *>(&tail.item_t0[it_par]);
+                }
+                const int t = item_tile(ti, t0, t_lo, t_hi);
                 const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
                 const int tile0 = t * TC_BN;
                 const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
@@ -232,6 +251,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 as ^= 1;
                 if (as == 0) acc_ph ^= 1;
             }
+            it_par ^= 1;
             if (valid) {
                 args.cand_cnt[slot] = cnt;
                 args.cand_tau[slot] = tau;

@@ -290,6 +290,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         uint32_t acc_ph = 0;
         unsigned ctr[4] = {0, 0, 0, 0};
         long long t_wait = 0, t_work = 0;
+        long long tprof[4] = {0, 0, 0, 0};
         int it_par = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -333,7 +334,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 };
                 if (args.debug_mode != 1)
                     filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
-                                      args.debug_mode, nullptr, tau, cnt, list, ctr, release);
+                                      args.debug_mode, nullptr, tau, cnt, list, ctr, release,
+                                      args.debug_mode == 9 ? tprof : nullptr);
                 else
                     release();
                 ctr[3] += TC_BN / 32;
@@ -352,6 +354,9 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
             atomicAdd(&scw->dbg[4], (unsigned long long)t_wait);
             atomicAdd(&scw->dbg[5], (unsigned long long)t_work);
+            if (args.debug_mode == 9)
+                for (int i = 0; i < 4; ++i)
+                    atomicAdd(&scw->cand_total[40 + i], (unsigned long long)tprof[i]);
         }
     }
 
@@ -819,7 +824,8 @@ int pick_L(int kcap, bool inexact) {
     if (L < 32) L = 32;
     return L;
 }
-int pick_gcap(int L) { return L <= 32 ? 128 : (L <= 64 ? 256 : 512); }
+// list capacity: the filter checks it once per tile, after up to TC_BN (128) appends
+int pick_gcap(int L) { return L <= 96 ? 256 : 512; }
 
 template <int GCAP>
 size_t tc2_smem_bytes(const TcPlan &p) {
@@ -1128,6 +1134,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                     hsc.dbg[0], hsc.dbg[1], hsc.dbg[2], hsc.dbg[3], (double)hsc.dbg[4],
                     (double)hsc.dbg[5], (double)hsc.dbg[6], (double)hsc.dbg[7],
                     (double)hsc.cand_total[63]);
+            fprintf(stderr, "tc dbg: filter_tile cycles: load+maxima %.3g release(no hit) %.3g slow %.3g hard-shrink %.3g\n",
+                    (double)hsc.cand_total[40], (double)hsc.cand_total[41], (double)hsc.cand_total[42],
+                    (double)hsc.cand_total[43]);
         if (ev) {
             cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);
             cudaEventElapsedTime(&times->ms_gemm, ev[1], ev[2]);

@@ -128,17 +128,18 @@ __device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lan
 #pragma unroll 1
     for (int it = 0; it < 32; ++it) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
+        // count by ballots: VOTE + POPC stay on the ordinary pipes, a REDUX per step does not
         int c = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) c += ((uint32_t)(k[i] >> 32) <= mid) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
+        for (int i = 0; i < PER; ++i)
+            c += __popc(__ballot_sync(0xffffffffu, (uint32_t)(k[i] >> 32) <= mid));
         if (c >= L) hi = mid; else lo = mid + 1;
     }
     const uint32_t x = lo;  // L-th smallest ordered score
     int c_lt = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) c_lt += ((uint32_t)(k[i] >> 32) < x) ? 1 : 0;
-    c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+    for (int i = 0; i < PER; ++i)
+        c_lt += __popc(__ballot_sync(0xffffffffu, (uint32_t)(k[i] >> 32) < x));
     int quota = L - c_lt;  // how many of the keys with score == x survive
     __syncwarp();          // all loads done before the list is overwritten
     int base = 0;
@@ -180,76 +181,95 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
 
 // Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
 // it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
-// The whole 32 x 128 slice is first copied to registers (two 64-column tcgen05.ld in flight
-// together) and the accumulator stage is released to the tensor cores IMMEDIATELY
-// (`release`): everything whose duration varies -- scanning hit groups, appending, shrinking --
-// then works from registers and never delays the next MMA.
-// A thread keeps its row's running threshold tau and appends every score above it to the row's
-// candidate list; full lists are shrunk to the L best (shrink_row) and tau raised.
+//
+// Hot path (kept small and contiguous -- it must live in the instruction cache): copy the
+// 32 x 128 slice to registers with two 64-column tcgen05.ld in flight together, reduce it to
+// 16 group maxima (groups of 8 columns) with 3-input max, compare with the row's threshold tau
+// and OR the 16-bit result over the warp.  No bit set (the common case): release the
+// accumulator stage and return.
+// Slow path (one small loop, no unrolled copies): for every flagged group re-read its 8 columns
+// from TMEM by address and append the scores above tau to the row's candidate list with
+// predicated stores (no divergent branches); then release the stage, then -- rarely -- shrink a
+// list that reached its hard capacity.
 // tau_shared (pair kernel): ordered bits of the threshold shared by the two threads that
 // filter the two column halves of the same row.
 template <int GCAP, class Release>
 __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
                                             int self, int L, int lane, int debug_mode,
                                             uint32_t *tau_shared, float &tau, int &cnt,
-                                            key64_t *list, unsigned (&ctr)[4], Release release) {
-    const int trigger = GCAP - 32;  // hard limit; soft shrinks happen in idle time
-    const int id_lim = special ? ib_hi : 0x7fffffff;
-    uint32_t ra[64], rb[64];
-    ptx::tmem_ld_32x32b_x64(tbase, ra);
-    ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
-    ptx::tmem_wait_ld();
-    release();
+                                            key64_t *list, unsigned (&ctr)[4], Release release,
+                                            long long *tprof = nullptr) {
+    const long long tp0 = tprof ? clock64() : 0;
+    unsigned gmask = 0;
+    {
+        uint32_t ra[64], rb[64];
+        ptx::tmem_ld_32x32b_x64(tbase, ra);
+        ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+        ptx::tmem_wait_ld();
 #pragma unroll
-    for (int c = 0; c < TC_BN / 32; ++c) {
-        uint32_t(&buf)[64] = (c < 2) ? ra : rb;
-        const int o32 = (c & 1) * 32;
-        unsigned gmask = 0;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            const int o = o32 + q4 * 8;
+        for (int q = 0; q < 16; ++q) {
+            uint32_t(&buf)[64] = (q < 8) ? ra : rb;
+            const int o = (q & 7) * 8;
             float m = ptx::fmax3(__uint_as_float(buf[o]), __uint_as_float(buf[o + 1]),
                                  __uint_as_float(buf[o + 2]));
             m = ptx::fmax3(m, __uint_as_float(buf[o + 3]), __uint_as_float(buf[o + 4]));
             m = ptx::fmax3(m, __uint_as_float(buf[o + 5]), __uint_as_float(buf[o + 6]));
             m = fmaxf(m, __uint_as_float(buf[o + 7]));
-            gmask |= (m > tau) ? (1u << q4) : 0u;
+            gmask |= (m > tau) ? (1u << q) : 0u;
         }
-        // groups of 8 columns in which some row of this warp has a candidate
-        const unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
-        if (groups != 0 && debug_mode != 2) {
-            ++ctr[0];
-            const int col0 = col_base + c * 32;
-            // Branch-free scan of the flagged groups: divergent branches cost ~25 cycles each
-            // on this path, a predicated store costs one issue slot.
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                if (groups & (1u << q4)) {  // warp-uniform
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t u = buf[o32 + q4 * 8 + j];
-                        const int id = col0 + q4 * 8 + j;
-                        const bool p = (__uint_as_float(u) > tau) & (id < id_lim) & (id != self);
-                        append_if(p, list, cnt, u, id);
-                    }
-                }
-            }
-            unsigned need = __ballot_sync(0xffffffffu, cnt > trigger);
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                key64_t *l = reinterpret_cast<key64_t *>(
-                    __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
-                ++ctr[1];
-                if (lane == src) {
-                    cnt = L;
-                    tau = fmaxf(tau, -ordered_to_float(x));
-                    if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
-                }
-            }
+    }
+    // groups of 8 columns in which some row of this warp has a candidate
+    unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
+    const long long tp1 = tprof ? clock64() : 0;
+    if (groups == 0 || debug_mode == 2) {
+        release();
+        if (tprof) {
+            tprof[0] += tp1 - tp0;
+            tprof[1] += clock64() - tp1;
         }
+        return;
+    }
+    ++ctr[0];
+    const int id_lim = special ? ib_hi : 0x7fffffff;
+#pragma unroll 1
+    do {
+        const int q = __ffs(groups) - 1;
+        groups &= groups - 1;
+        uint32_t v8[8];
+        ptx::tmem_ld_32x32b_x8(tbase + q * 8, v8);
+        ptx::tmem_wait_ld();
+        const int col0 = col_base + q * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int id = col0 + j;
+            const bool p = (__uint_as_float(v8[j]) > tau) & (id < id_lim) & (id != self);
+            append_if(p, list, cnt, v8[j], id);
+        }
+    } while (groups != 0);
+    release();
+    if (cnt > GCAP) __trap();  // list overflow would silently corrupt a neighbouring row's list
+    const long long tp2 = tprof ? clock64() : 0;
+    // hard capacity: a tile can append up to TC_BN entries before this check runs again
+    unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - TC_BN);
+#pragma unroll 1
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        key64_t *l = reinterpret_cast<key64_t *>(
+            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+        const int n = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
+        ++ctr[1];
+        if (lane == src) {
+            cnt = L;
+            tau = fmaxf(tau, -ordered_to_float(x));
+            if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
+        }
+    }
+    if (tprof) {
+        tprof[0] += tp1 - tp0;          // TMEM -> registers, group maxima
+        tprof[2] += tp2 - tp1;          // slow path up to the release
+        tprof[3] += clock64() - tp2;    // hard shrinks
     }
 }
 
@@ -262,7 +282,7 @@ __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32
                                                            int lane, uint32_t *tau_shared,
                                                            float &tau, int &cnt, key64_t *list,
                                                            unsigned (&ctr)[4]) {
-    const int soft = (L + L / 2 < GCAP - 32) ? L + L / 2 : GCAP - 32;
+    const int soft = (L + L / 2 < GCAP - TC_BN) ? L + L / 2 : GCAP - TC_BN;
     while (!ptx::mbar_test_wait(bar, parity)) {
         const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
         if (need == 0) {

@@ -37,6 +37,8 @@ class Stats(C.Structure):
         ("ms_rerank", C.c_double),
         ("ms_exact", C.c_double),
         ("candidates", C.c_double),
+        ("eps_ratio_max", C.c_double),
+        ("inexact_operands", C.c_longlong),
     ]
 
 

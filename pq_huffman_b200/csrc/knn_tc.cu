@@ -621,6 +621,8 @@ struct RerankArgs {
     const int *cand_cnt;
     const float *cand_tau;
     const double *qnorm64;  // |x|^2 of the query rows, indexed like queries (q_row_begin + r)
+    const double *bnorm64;  // |y|^2 of the base rows
+    int check_eps;          // debug: measure |S'_tensor - S'_fp64| / eps over all candidates
     const PrepScalars *sc;
     int ksteps;             // UMMA K steps per accumulator (for the accumulation bound)
     int *assign;
@@ -654,6 +656,38 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
     const float *qsrc = a.queries + (size_t)(a.q_row_begin + r) * a.d;
     for (int i = lane; i < a.d; i += 32) qrow[i] = qsrc[i];
     __syncwarp();
+
+    // error bound of the tensor-core score for this row (see the certificate below)
+    double eps = 0.0;
+    const double sigma = (double)scale_from_maxabs_bits(a.sc->maxabs_bits);
+    const double xn2 = a.qnorm64[a.q_row_begin + r];
+    {
+        const double ymax = (double)__uint_as_float(a.sc->ymax_bits);
+        const double xn = sqrt(xn2) * sigma * (1.0 + 1e-12);
+        const double u = 1.0 / 2048.0;  // fp16 unit roundoff 2^-11
+        if (a.sc->inexact)
+            eps += (2.0 * u + u * u) * xn * ymax + (double)a.d * (1.0 / 32768.0);
+        eps += (double)a.ksteps * (1.0 / 4194304.0) * (xn * ymax + 0.5 * ymax * ymax);
+        eps += ymax * ymax * (1.0 / 536870912.0);
+    }
+    if (a.check_eps) {
+        // debug: the bound must dominate the real error of every score the kernel produced
+        float worst = 0.0f;
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t id = key_pos(keys[i]);
+            const float s_tc = -key_score(keys[i]);
+            const float *brow = a.base + (size_t)id * a.d;
+            double dot = 0.0;
+            for (int j = 0; j < a.d; ++j) dot += (double)qrow[j] * (double)brow[j];
+            const double s_true = sigma * sigma * (dot - 0.5 * a.bnorm64[id]);
+            const double err = fabs((double)s_tc - s_true);
+            const float ratio = eps > 0.0 ? (float)(err / eps) : (err > 0.0 ? 1e30f : 0.0f);
+            worst = fmaxf(worst, ratio);
+        }
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0)
+            atomicMax(const_cast<uint32_t *>(&a.sc->pad[0]), __float_as_uint(worst));
+    }
 
     // exact distances: the scalar sequence of get_real_dist, one candidate per lane
     for (int i = lane; i < n; i += 32) {
@@ -690,16 +724,6 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         if (m < a.kcap) {
             ok = false;  // cannot happen (a threshold implies >= L >= kcap candidates)
         } else {
-            const double sigma = (double)scale_from_maxabs_bits(a.sc->maxabs_bits);
-            const double ymax = (double)__uint_as_float(a.sc->ymax_bits);
-            const double xn2 = a.qnorm64[a.q_row_begin + r];
-            const double xn = sqrt(xn2) * sigma * (1.0 + 1e-12);
-            const double u = 1.0 / 2048.0;  // fp16 unit roundoff 2^-11
-            double eps = 0.0;
-            if (a.sc->inexact)
-                eps += (2.0 * u + u * u) * xn * ymax + (double)a.d * (1.0 / 32768.0);
-            eps += (double)a.ksteps * (1.0 / 4194304.0) * (xn * ymax + 0.5 * ymax * ymax);
-            eps += ymax * ymax * (1.0 / 536870912.0);
             const double gamma = (double)(a.d + 2) * (1.0 / 16777216.0) * 1.0001;
             const double lb =
                 (xn2 * (1.0 - 1e-12) - 2.0 * ((double)tau + eps) / (sigma * sigma)) * (1.0 - gamma);
@@ -1088,6 +1112,8 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     ra.cand_cnt = cnt;
     ra.cand_tau = tau;
     ra.qnorm64 = self_join ? norm_b : norm_q - q_src0;  // indexed by q_row_begin + r
+    ra.bnorm64 = norm_b;
+    ra.check_eps = getenv("PQH_TC_CHECK_EPS") ? 1 : 0;
     ra.sc = sc;
     ra.ksteps = (lo.d16 + FOLD_COLS) / 16;
     ra.assign = d_assign;
@@ -1126,6 +1152,11 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         times->candidates = 0;
         for (int i = 0; i < 32; ++i) times->candidates += (double)hsc.cand_total[i];
         times->inexact = (int)hsc.inexact;
+        {
+            union { uint32_t u; float f; } cv;
+            cv.u = hsc.pad[0];
+            times->eps_ratio_max = cv.f;
+        }
         if (getenv("PQH_TC_DEBUG"))
             fprintf(stderr,
                     "tc dbg: slow_chunks=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu | "

@@ -244,6 +244,8 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
             st->ms_gemm += tt.ms_gemm;
             st->ms_rerank += tt.ms_rerank;
             st->candidates += tt.candidates;
+            if (tt.eps_ratio_max > st->eps_ratio_max) st->eps_ratio_max = tt.eps_ratio_max;
+            st->inexact_operands = tt.inexact;
         }
         rows_tc = n_rows - (long long)n_fb;
         if (n_fb > 0) {
@@ -386,6 +388,8 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, const f
             if (sts[g].ms_rerank > st.ms_rerank) st.ms_rerank = sts[g].ms_rerank;
             if (sts[g].ms_exact > st.ms_exact) st.ms_exact = sts[g].ms_exact;
             st.candidates += sts[g].candidates;
+            if (sts[g].eps_ratio_max > st.eps_ratio_max) st.eps_ratio_max = sts[g].eps_ratio_max;
+            st.inexact_operands |= sts[g].inexact_operands;
         }
     }
     st.ms_total =

@@ -97,6 +97,53 @@ def test_row_slices_tile_the_full_result(oracle, algo):
         assert_rows_equal((a, d), (full[0][lo:hi], full[1][lo:hi]))
 
 
+def test_certificate_failure_falls_back_to_exact(oracle):
+    """Data the FP16 tensor-core pass cannot resolve: all points within 1e-3 of a large common
+    offset, so FP16 rounding (ulp 2^-7 at 10.0) swamps every difference.  The certificate must
+    refuse those rows and the exact kernel must redo them; the answer stays bit-exact."""
+    rng = np.random.default_rng(5)
+    x = (10.0 + 1e-3 * rng.normal(size=(4000, 64))).astype(np.float32)
+    knn.set_algo(knn.ALGO_AUTO)
+    got = knn.knn_full_thread(x, None, 9)
+    st = knn.last_stats()
+    assert st["rows_exact"] > 0, "expected the certificate to reject rows on this input"
+    assert st["rows_tensor"] + st["rows_exact"] == 4000
+    assert_rows_equal(got, oracle.knn(x, None, 9))
+
+
+def test_mixed_certified_and_fallback_rows(oracle):
+    """Half the set is well separated (certifies), half is the degenerate cloud above."""
+    rng = np.random.default_rng(6)
+    a = synth.sift_like(2500, 64, seed=12)
+    b = (100.0 + 1e-2 * rng.normal(size=(2500, 64))).astype(np.float32)
+    x = np.ascontiguousarray(np.concatenate([a, b])[rng.permutation(5000)])
+    got = knn.knn_full_thread(x, None, 12)
+    st = knn.last_stats()
+    assert 0 < st["rows_exact"] < 5000 and st["rows_tensor"] > 0
+    assert_rows_equal(got, oracle.knn(x, None, 12))
+
+
+@pytest.mark.parametrize("gen,n,d,k", [("sift", 6000, 128, 17), ("gist", 4000, 960, 17),
+                                       ("deep", 6000, 96, 33), ("uniform", 5000, 272, 9),
+                                       ("gist", 5000, 100, 17)])
+def test_certificate_error_bound_dominates_real_error(monkeypatch, gen, n, d, k):
+    """The certificate assumes |tensor score - true score| <= eps (FP16 rounding + the tensor
+    core's FP32 accumulation).  Measure the real error of every candidate score against an FP64
+    dot product on the device and check that the bound holds with room to spare."""
+    monkeypatch.setenv("PQH_TC_CHECK_EPS", "1")
+    x = {"sift": synth.sift_like, "gist": synth.gist_like, "deep": synth.deep_like,
+         "uniform": synth.uniform}[gen](n, d, seed=7 * n + d)
+    knn.knn_full_thread(x, None, k)
+    st = knn.last_stats()
+    assert st["rows_tensor"] > 0
+    assert st["eps_ratio_max"] <= 1.0, st
+    if gen == "sift":
+        assert st["inexact_operands"] == 0      # integer data: FP16 operands are exact
+        assert st["eps_ratio_max"] == 0.0       # ... and so is the tensor-core accumulation
+    else:
+        assert st["inexact_operands"] == 1
+
+
 def test_stats_report_launches(oracle):
     x = synth.sift_like(2000, 128, seed=6)
     knn.knn_full_thread(x, None, 17)
@@ -120,3 +167,23 @@ def test_medium_property_100k():
     for r in rows:
         ea, ed = orc.knn_rows(x, None, 17, int(r), int(r) + 1)
         assert np.array_equal(a[r], ea[0]) and np.array_equal(d[r], ed[0])
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif(_n_devices() < 2, reason="needs two GPUs")
+def test_in_library_multi_gpu_row_split(oracle):
+    """PQH_DEVICES-style context over two GPUs: knn_full_thread splits the query rows, every
+    device gets the base over its own link, results land in the caller's arrays."""
+    x = synth.sift_like(30000, 128, seed=44)
+    try:
+        knn.init([0, 1])
+        got = knn.knn_full_thread(x, None, 17)
+        st = knn.last_stats()
+        assert st["rows"] == 30000
+    finally:
+        knn.init([0])
+    assert_rows_equal(got, oracle.knn(x, None, 17))

@@ -171,7 +171,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -345,9 +345,30 @@ def run_ours(args):
                 "value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                 "sample": f"{srows} query rows x full {n}-row base in {dt:.1f} s "
                           "(oracle/knn_blas.c, Yael-shaped sgemm + heaps)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, OpenBLAS warnings) print to fd 1; the contract is ONE
+    JSON line on stdout.  Everything else goes to stderr; emit() writes the line to the real fd."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -360,6 +381,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -914,11 +914,23 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     const int qrows = lo->variant == 3 ? 512 : TC_ROWS;  // query rows per work item
     lo->n_qtiles = (n_rows + qrows - 1) / qrows;
     lo->n_btiles = (nb + bn - 1) / bn;
-    int nsplit = 1;
+    // Base splits: a work item is (query tile, base split).  Splitting the base gives more, shorter
+    // items -- worth it when the query tiles alone do not fill the SMs evenly (the last round of
+    // a persistent grid is otherwise partly idle), at the price of one candidate list per split.
     const int max_lists = 2048 / lo->gcap;
-    while (nsplit * 2 * lo->halves <= max_lists && nsplit < 4 &&
-           lo->n_qtiles * nsplit < 2 * units && lo->n_btiles / (nsplit * 2) >= 8)
-        nsplit *= 2;
+    int nsplit = 1;
+    double best = 0.0;
+    for (int s = 1; s <= 4; s *= 2) {
+        if (s * lo->halves > max_lists) break;
+        if (s > 1 && lo->n_btiles / s < 16) break;
+        const long long items = (long long)lo->n_qtiles * s;
+        const long long rounds = (items + units - 1) / units;
+        const double eff = (double)items / (double)(rounds * units);
+        if (eff > best + 0.03) {  // prefer fewer splits unless the gain is real
+            best = eff;
+            nsplit = s;
+        }
+    }
     lo->nsplit = nsplit;
     lo->nlists = nsplit * lo->halves;
     lo->tiles_per_split = (lo->n_btiles + nsplit - 1) / nsplit;
@@ -1157,7 +1169,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             cv.u = hsc.pad[0];
             times->eps_ratio_max = cv.f;
         }
-        if (getenv("PQH_TC_DEBUG"))
+        if (getenv("PQH_TC_DEBUG")) {
             fprintf(stderr,
                     "tc dbg: slow_chunks=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu | "
                     "epi warps: wait %.3g work %.3g cyc | mma thread: wait_b %.3g wait_acc %.3g "
@@ -1168,6 +1180,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             fprintf(stderr, "tc dbg: filter_tile cycles: load+maxima %.3g release(no hit) %.3g slow %.3g hard-shrink %.3g\n",
                     (double)hsc.cand_total[40], (double)hsc.cand_total[41], (double)hsc.cand_total[42],
                     (double)hsc.cand_total[43]);
+        }
         if (ev) {
             cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);
             cudaEventElapsedTime(&times->ms_gemm, ev[1], ev[2]);

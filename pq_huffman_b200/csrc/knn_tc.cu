@@ -931,6 +931,10 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
             nsplit = s;
         }
     }
+    if (const char *e = getenv("PQH_TC_NSPLIT")) {
+        const int v = atoi(e);
+        if (v >= 1 && v * lo->halves <= max_lists && lo->n_btiles / v >= 8) nsplit = v;
+    }
     lo->nsplit = nsplit;
     lo->nlists = nsplit * lo->halves;
     lo->tiles_per_split = (lo->n_btiles + nsplit - 1) / nsplit;

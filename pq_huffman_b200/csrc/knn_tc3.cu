@@ -376,11 +376,12 @@ knn_tc3_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     if (n > trigger) {  // not already shrunk for an earlier lane of this batch
                         const size_t slot = (size_t)(r0 + srow) * args.nsplit + sp;
                         key64_t *l = args.cand + slot * GCAP;
+                        int kept;
                         const uint32_t x = (GCAP > 128 && n <= 128)
-                                               ? shrink_row<128>(l, n, L, lane)
-                                               : shrink_row<GCAP>(l, n, L, lane);
+                                               ? shrink_row<128>(l, n, L, lane, kept)
+                                               : shrink_row<GCAP>(l, n, L, lane, kept);
                         if (lane == 0) {
-                            sm.cnt[g * 128 + srow] = L;
+                            sm.cnt[g * 128 + srow] = kept;
                             const float t_new = -ordered_to_float(x);
                             const float t_old = sm.tau[g * 128 + srow];
                             *reinterpret_cast<volatile float *>(&sm.tau[g * 128 + srow]) =

@@ -111,37 +111,64 @@ __host__ __device__ __forceinline__ float scale_from_maxabs_bits(uint32_t bits) 
 #endif
 }
 
-// Warp-cooperative shrink of one row's candidate list (n <= GCAP keys in global memory) to
-// its L best: a 32-step binary search on the ordered score bits finds the L-th best score,
-// survivors are written back compacted (unsorted).  Returns that score's ordered bits: every
-// dropped key has a score that is not better.  No sort, no shared memory.
-template <int GCAP>
-__device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lane) {
-    constexpr int PER = GCAP / 32;
+// Warp-cooperative shrink of one row's candidate list (n <= NMAX keys in global memory) to its
+// best L .. L+L/2 keys.  A bisection on the ordered score bits, bracketed by the list's own
+// min/max and counted with ballots, stops at the first pivot that keeps between L and 1.5 L keys
+// (typically < 10 steps); only when equal scores make that impossible does it run to the exact
+// L-th score and break the tie by position in the list.  Survivors are written back compacted
+// (unsorted); new_cnt receives their number.  Returns the pivot's ordered bits: every dropped
+// key has a strictly worse score.  Registers, ballots and two warp reductions only -- no
+// shared memory, no sort: a shrink has to cost about one tile time, not several.
+template <int NMAX>
+__device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lane, int &new_cnt) {
+    constexpr int PER = NMAX / 32;
     key64_t k[PER];
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int idx = i * 32 + lane;
         k[i] = idx < n ? __ldcg(list + idx) : KEY_INF;
+        const uint32_t h = (uint32_t)(k[i] >> 32);
+        if (idx < n) {
+            mn = h < mn ? h : mn;
+            mx = h > mx ? h : mx;
+        }
     }
-    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+    uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+    const int Lmax = L + L / 2;
+    bool early = false;
+    uint32_t x = hi;
+    int c_keep = n;
 #pragma unroll 1
-    for (int it = 0; it < 32; ++it) {
+    while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
-        // count by ballots: VOTE + POPC stay on the ordinary pipes, a REDUX per step does not
         int c = 0;
 #pragma unroll
         for (int i = 0; i < PER; ++i)
             c += __popc(__ballot_sync(0xffffffffu, (uint32_t)(k[i] >> 32) <= mid));
-        if (c >= L) hi = mid; else lo = mid + 1;
+        if (c >= L) {
+            if (c <= Lmax) {
+                early = true;
+                x = mid;
+                c_keep = c;
+                break;
+            }
+            hi = mid;
+        } else {
+            lo = mid + 1;
+        }
     }
-    const uint32_t x = lo;  // L-th smallest ordered score
-    int c_lt = 0;
+    int quota = 0x7fffffff;  // keys with score == x that survive (all of them on the early path)
+    if (!early) {
+        x = lo;  // exact L-th smallest ordered score; ties at x are cut by list position
+        int c_lt = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i)
-        c_lt += __popc(__ballot_sync(0xffffffffu, (uint32_t)(k[i] >> 32) < x));
-    int quota = L - c_lt;  // how many of the keys with score == x survive
-    __syncwarp();          // all loads done before the list is overwritten
+        for (int i = 0; i < PER; ++i)
+            c_lt += __popc(__ballot_sync(0xffffffffu, (uint32_t)(k[i] >> 32) < x));
+        quota = L - c_lt;
+        c_keep = L;
+    }
+    __syncwarp();  // all loads done before the list is overwritten
     int base = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -154,12 +181,12 @@ __device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lan
         if (keep) __stcg(list + base + __popc(kb & lt_mask), k[i]);
         base += __popc(kb);
         const int taken = __popc(eq);
-        quota -= taken < quota ? taken : quota;
+        if (!early) quota -= taken < quota ? taken : quota;
     }
     __syncwarp();
+    new_cnt = c_keep < base ? c_keep : base;
     return x;
 }
-
 
 // Predicated append of (ordered(-score), id) to a row's candidate list: no branch.
 __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint32_t score_bits,
@@ -258,10 +285,11 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
         key64_t *l = reinterpret_cast<key64_t *>(
             __shfl_sync(0xffffffffu, (unsigned long long)list, src));
         const int n = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t x = shrink_row<GCAP>(l, n, L, lane);
+        int kept;
+        const uint32_t x = shrink_row<GCAP>(l, n, L, lane, kept);
         ++ctr[1];
         if (lane == src) {
-            cnt = L;
+            cnt = kept;
             tau = fmaxf(tau, -ordered_to_float(x));
             if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
         }
@@ -293,11 +321,13 @@ __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32
         key64_t *l = reinterpret_cast<key64_t *>(
             __shfl_sync(0xffffffffu, (unsigned long long)list, src));
         const int n = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t x = (GCAP > 128 && n <= 128) ? shrink_row<128>(l, n, L, lane)
-                                                    : shrink_row<GCAP>(l, n, L, lane);
+        int kept;
+        const uint32_t x = n <= 64    ? shrink_row<64>(l, n, L, lane, kept)
+                           : n <= 128 ? shrink_row<128>(l, n, L, lane, kept)
+                                      : shrink_row<GCAP>(l, n, L, lane, kept);
         ++ctr[2];
         if (lane == src) {
-            cnt = L;
+            cnt = kept;
             tau = fmaxf(tau, -ordered_to_float(x));
             if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
         }

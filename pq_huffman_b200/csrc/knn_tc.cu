@@ -914,23 +914,15 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     const int qrows = lo->variant == 3 ? 512 : TC_ROWS;  // query rows per work item
     lo->n_qtiles = (n_rows + qrows - 1) / qrows;
     lo->n_btiles = (nb + bn - 1) / bn;
-    // Base splits: a work item is (query tile, base split).  Splitting the base gives more, shorter
-    // items -- worth it when the query tiles alone do not fill the SMs evenly (the last round of
-    // a persistent grid is otherwise partly idle), at the price of one candidate list per split.
+    // Base splits: a work item is (query tile, base split).  A split costs a second candidate list
+    // per row with its own warm-up (measured: 100k x 128 takes 5.0 / 6.7 / 8.6 ms with 1 / 2 / 4
+    // splits although 4 splits fill the last round of the grid best), so the base is only split
+    // when the query tiles alone cannot occupy every SM once.
     const int max_lists = 2048 / lo->gcap;
     int nsplit = 1;
-    double best = 0.0;
-    for (int s = 1; s <= 4; s *= 2) {
-        if (s * lo->halves > max_lists) break;
-        if (s > 1 && lo->n_btiles / s < 16) break;
-        const long long items = (long long)lo->n_qtiles * s;
-        const long long rounds = (items + units - 1) / units;
-        const double eff = (double)items / (double)(rounds * units);
-        if (eff > best + 0.03) {  // prefer fewer splits unless the gain is real
-            best = eff;
-            nsplit = s;
-        }
-    }
+    while (lo->n_qtiles * nsplit < units && nsplit * 2 * lo->halves <= max_lists && nsplit < 4 &&
+           lo->n_btiles / (nsplit * 2) >= 16)
+        nsplit *= 2;
     if (const char *e = getenv("PQH_TC_NSPLIT")) {
         const int v = atoi(e);
         if (v >= 1 && v * lo->halves <= max_lists && lo->n_btiles / v >= 8) nsplit = v;

@@ -423,7 +423,7 @@ knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tail.acc_full[i], 1);
-            ptx::mbar_init(&tail.acc_empty[i], 2 * TC_EPI_WARPS);
+            ptx::mbar_init(&tail.acc_empty[i], 2 * 4);  // 4 filter warps in each CTA
         }
         ptx::fence_barrier_init();
     }
@@ -525,18 +525,14 @@ knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 ptx::umma_commit_2sm(&tail.a_empty);
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ===================== epilogue: threshold filter =====================
-        const int e = warp - 2;
-        const int half = e >> 2;    // which 128 of the tile's 256 columns this warp filters
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        // four filter warps (one per TMEM lane quadrant); a thread owns one query row and
+        // filters all 256 columns of a tile as two 128-column passes
+        const int quad = warp & 3;
         const int row_in_cta = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        // each column half keeps half of the row's L (never fewer than the neighbours asked
-        // for): the union of the two halves' best kcap always contains the row's best kcap
-        const int L_row = args.sc->inexact ? args.L_inexact : args.L_exact;
-        const int L = (L_row / 2 > args.kcap) ? L_row / 2 : args.kcap;
-        uint32_t *tau_sh = &tail.tau_shared[row_in_cta];
+        const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
         uint32_t acc_empty_l[2];
         acc_empty_l[0] = ptx::mapa_u32(ptx::smem_u32(&tail.acc_empty[0]), 0);
         acc_empty_l[1] = ptx::mapa_u32(ptx::smem_u32(&tail.acc_empty[1]), 0);
@@ -552,43 +548,40 @@ knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             const int r = qt * TC_ROWS + (int)rank * 128 + row_in_cta;
             const bool valid = r < args.n_rows;
             const int self = (valid && args.self_join) ? args.q_begin + r : -1;
-            const size_t slot = valid ? ((size_t)r * args.nsplit + sp) * 2 + half : 0;
+            const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
             key64_t *list = args.cand + slot * GCAP;
             float tau = valid ? NEG_INF : POS_INF;
             int cnt = 0;
-            // the two column halves of a row share one threshold (epilogue-only named barrier
-            // orders the reset against the other half's last use in the previous item)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0) *tau_sh = float_to_ordered(NEG_INF);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             long long b_hi = (long long)t_hi * 256;
             if (b_hi > args.nb) b_hi = args.nb;
             const int ib_hi = (int)b_hi;
 
             for (int t = t_lo; t < t_hi; ++t) {
-                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, tau_sh, tau,
+                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
                                                  cnt, list, ctr);
                 ptx::tc_fence_after_sync();
-                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + half * 128);
+                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256);
                 const int tile0 = t * 256;
                 const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + 256);
-                if (valid) tau = fmaxf(tau, ordered_to_float(*(volatile uint32_t *)tau_sh));
                 auto release = [&]() {
                     ptx::tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_l[as]);
                 };
-                if (args.debug_mode != 1)
-                    filter_tile<GCAP>(tbase, tile0 + half * 128, special, ib_hi, self, L, lane,
-                                      args.debug_mode, tau_sh, tau, cnt, list, ctr, release);
-                else
+                auto keep = []() {};
+                if (args.debug_mode != 1) {
+                    filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
+                                      args.debug_mode, nullptr, tau, cnt, list, ctr, keep);
+                    filter_tile<GCAP>(tbase + 128, tile0 + 128, special, ib_hi, self, L, lane,
+                                      args.debug_mode, nullptr, tau, cnt, list, ctr, release);
+                } else {
                     release();
+                }
                 ctr[3] += TC_BN / 32;
                 as ^= 1;
                 if (as == 0) acc_ph ^= 1;
             }
             if (valid) {
-                tau = fmaxf(tau, ordered_to_float(*(volatile uint32_t *)tau_sh));
                 args.cand_cnt[slot] = cnt;
                 args.cand_tau[slot] = tau;
             }
@@ -908,7 +901,7 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->L_exact = pick_L(kcap, false);
     lo->gcap = pick_gcap(lo->L);
     lo->variant = tc_pick_variant(lo->d16, lo->gcap);
-    lo->halves = lo->variant == 2 ? 2 : 1;
+    lo->halves = 1;
     const int bn = lo->variant == 2 ? 256 : TC_BN;
     const int units = lo->variant == 1 ? num_sms : num_sms / 2;
     const int qrows = lo->variant == 3 ? 512 : TC_ROWS;  // query rows per work item

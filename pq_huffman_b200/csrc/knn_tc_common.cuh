@@ -227,12 +227,14 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
                                             key64_t *list, unsigned (&ctr)[4], Release release,
                                             long long *tprof = nullptr) {
     const long long tp0 = tprof ? clock64() : 0;
-    unsigned gmask = 0;
+    unsigned groups = 0;
     {
         uint32_t ra[64], rb[64];
         ptx::tmem_ld_32x32b_x64(tbase, ra);
         ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
         ptx::tmem_wait_ld();
+        // 16 group maxima (groups of 8 columns), then the row maximum
+        float gm[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             uint32_t(&buf)[64] = (q < 8) ? ra : rb;
@@ -241,12 +243,20 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
                                  __uint_as_float(buf[o + 2]));
             m = ptx::fmax3(m, __uint_as_float(buf[o + 3]), __uint_as_float(buf[o + 4]));
             m = ptx::fmax3(m, __uint_as_float(buf[o + 5]), __uint_as_float(buf[o + 6]));
-            m = fmaxf(m, __uint_as_float(buf[o + 7]));
-            gmask |= (m > tau) ? (1u << q) : 0u;
+            gm[q] = fmaxf(m, __uint_as_float(buf[o + 7]));
+        }
+        float rm = ptx::fmax3(gm[0], gm[1], gm[2]);
+#pragma unroll
+        for (int q = 3; q < 15; q += 2) rm = ptx::fmax3(rm, gm[q], gm[q + 1]);
+        rm = fmaxf(rm, gm[15]);
+        // common case: no row of the warp has anything above its threshold -> one vote, done
+        if (__any_sync(0xffffffffu, rm > tau)) {
+            unsigned gmask = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
+            groups = __reduce_or_sync(0xffffffffu, gmask);
         }
     }
-    // groups of 8 columns in which some row of this warp has a candidate
-    unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
     const long long tp1 = tprof ? clock64() : 0;
     if (groups == 0 || debug_mode == 2) {
         release();

@@ -99,6 +99,17 @@ int pqh_knn_search_rows(int nq_total, int nb, int d, int k, const float *b, cons
                         int self_join, int q_begin, int q_end, int *assign, float *dis);
 
 /*
+ * Same search with explicit leading dimensions (in floats) of the two host matrices: row i of
+ * b starts at b + i * ldb.  Lets a caller hand over vectors still interleaved with other data --
+ * e.g. an .fvecs file image, whose rows are [int32 d | d floats] (ldb = d + 1, b pointing one
+ * float into the buffer; the layout fast_nn_block_loader2.c:99-108 strips row by row) -- the
+ * library strips the padding in the H2D copy itself.
+ */
+int pqh_knn_search_rows_ld(int nq_total, int nb, int d, int k, const float *b, long long ldb,
+                           const float *v, long long ldv, int self_join, int q_begin, int q_end,
+                           int *assign, float *dis);
+
+/*
  * Device-resident variant for callers that already hold the vectors in HBM
  * (bench.py's device-timed arm, a future GPU loader): all pointers are device
  * pointers on `device`, the call is asynchronous on `stream` (a cudaStream_t

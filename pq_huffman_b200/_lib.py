@@ -14,6 +14,7 @@ EXPORTS = (
     "pqh_last_error",
     "pqh_knn_set_algo",
     "pqh_knn_search_rows",
+    "pqh_knn_search_rows_ld",
     "pqh_knn_workspace_bytes",
     "pqh_knn_search_device",
     "pqh_knn_last_stats",
@@ -71,6 +72,9 @@ def load():
     lib.pqh_knn_set_algo.restype = C.c_int
     lib.pqh_knn_search_rows.argtypes = [C.c_int] * 4 + [vp, vp] + [C.c_int] * 3 + [vp, vp]
     lib.pqh_knn_search_rows.restype = C.c_int
+    lib.pqh_knn_search_rows_ld.argtypes = ([C.c_int] * 4 + [vp, C.c_longlong, vp, C.c_longlong]
+                                           + [C.c_int] * 3 + [vp, vp])
+    lib.pqh_knn_search_rows_ld.restype = C.c_int
     lib.pqh_knn_workspace_bytes.argtypes = [C.c_int] * 4
     lib.pqh_knn_workspace_bytes.restype = C.c_longlong
     lib.pqh_knn_search_device.argtypes = (

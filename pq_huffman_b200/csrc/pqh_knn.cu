@@ -282,8 +282,8 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
 
 // Host-pointer search on one device.
 int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int k, const float *b,
-                     const float *v, int self_join, int q_begin, int q_end, int *assign,
-                     float *dis, pqh_knn_stats_t *st) {
+                     size_t ldb, const float *v, size_t ldv, int self_join, int q_begin, int q_end,
+                     int *assign, float *dis, pqh_knn_stats_t *st) {
     const int n_rows = q_end - q_begin;
     if (n_rows <= 0 || k <= 0) return PQH_OK;
     CU_TRY(cudaSetDevice(dc.dev));
@@ -297,8 +297,14 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
     if ((rc = dc.work.ensure(wbytes))) return rc;
 
     CU_TRY(cudaEventRecord(dc.ev[0], dc.stream));
-    if (base_bytes)
-        CU_TRY(cudaMemcpyAsync(dc.base.p, b, base_bytes, cudaMemcpyHostToDevice, dc.stream));
+    if (base_bytes) {
+        if (ldb == (size_t)d)
+            CU_TRY(cudaMemcpyAsync(dc.base.p, b, base_bytes, cudaMemcpyHostToDevice, dc.stream));
+        else  // strided rows (e.g. an .fvecs image): the copy engine drops the padding
+            CU_TRY(cudaMemcpy2DAsync(dc.base.p, (size_t)d * sizeof(float), b, ldb * sizeof(float),
+                                     (size_t)d * sizeof(float), (size_t)nb,
+                                     cudaMemcpyHostToDevice, dc.stream));
+    }
     const float *d_b = static_cast<const float *>(dc.base.p);
     const float *d_v = d_b;
     int q_row0 = 0;
@@ -306,8 +312,14 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
         // only the rows this call searches travel: row (q - q_begin) of the device copy
         const size_t qbytes = (size_t)n_rows * d * sizeof(float);
         if ((rc = dc.queries.ensure(qbytes))) return rc;
-        CU_TRY(cudaMemcpyAsync(dc.queries.p, v + (size_t)q_begin * d, qbytes,
-                               cudaMemcpyHostToDevice, dc.stream));
+        if (ldv == (size_t)d)
+            CU_TRY(cudaMemcpyAsync(dc.queries.p, v + (size_t)q_begin * d, qbytes,
+                                   cudaMemcpyHostToDevice, dc.stream));
+        else
+            CU_TRY(cudaMemcpy2DAsync(dc.queries.p, (size_t)d * sizeof(float),
+                                     v + (size_t)q_begin * ldv, ldv * sizeof(float),
+                                     (size_t)d * sizeof(float), (size_t)n_rows,
+                                     cudaMemcpyHostToDevice, dc.stream));
         d_v = static_cast<const float *>(dc.queries.p);
         q_row0 = q_begin;
     }
@@ -332,8 +344,8 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
     return PQH_OK;
 }
 
-int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, const float *v,
-                     int self_join, int q_begin, int q_end, int *assign, float *dis) {
+int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, size_t ldb, const float *v,
+                     size_t ldv, int self_join, int q_begin, int q_end, int *assign, float *dis) {
     int rc = check_args(nq_total, nb, d, k, b, v, q_begin, q_end, assign, dis);
     if (rc) return rc;
     if (self_join && nq_total != nb)
@@ -348,8 +360,8 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, const f
     const int n_rows = q_end - q_begin;
     const int G = (int)c->devs.size();
     if (G == 1 || n_rows < 2 * G) {
-        rc = search_rows_host(c, c->devs[0], nq_total, nb, d, k, b, v, self_join, q_begin, q_end,
-                              assign, dis, &st);
+        rc = search_rows_host(c, c->devs[0], nq_total, nb, d, k, b, ldb, v, ldv, self_join, q_begin,
+                              q_end, assign, dis, &st);
     } else {
         // query rows split evenly over the devices; each device
         // receives the base over its own PCIe link and returns its slice.
@@ -364,8 +376,8 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, const f
                 int lo = q_begin + g * per, hi = lo + per;
                 if (hi > q_end) hi = q_end;
                 if (lo >= hi) return;
-                rcs[g] = search_rows_host(c, c->devs[g], nq_total, nb, d, k, b, v, self_join, lo,
-                                          hi, assign + (size_t)(lo - q_begin) * k,
+                rcs[g] = search_rows_host(c, c->devs[g], nq_total, nb, d, k, b, ldb, v, ldv,
+                                          self_join, lo, hi, assign + (size_t)(lo - q_begin) * k,
                                           dis + (size_t)(lo - q_begin) * k, &sts[g]);
                 if (rcs[g]) errs[g] = g_err;
             });
@@ -433,7 +445,16 @@ int pqh_knn_set_algo(int algo) {
 
 int pqh_knn_search_rows(int nq_total, int nb, int d, int k, const float *b, const float *v,
                         int self_join, int q_begin, int q_end, int *assign, float *dis) {
-    return search_rows_impl(nq_total, nb, d, k, b, v, self_join, q_begin, q_end, assign, dis);
+    return search_rows_impl(nq_total, nb, d, k, b, (size_t)d, v, (size_t)d, self_join, q_begin,
+                            q_end, assign, dis);
+}
+
+int pqh_knn_search_rows_ld(int nq_total, int nb, int d, int k, const float *b, long long ldb,
+                           const float *v, long long ldv, int self_join, int q_begin, int q_end,
+                           int *assign, float *dis) {
+    if (ldb < d || ldv < d) return fail(PQH_EINVAL, "leading dimension smaller than d");
+    return search_rows_impl(nq_total, nb, d, k, b, (size_t)ldb, v, (size_t)ldv, self_join, q_begin,
+                            q_end, assign, dis);
 }
 
 long long pqh_knn_workspace_bytes(int nq, int nb, int d, int k) {
@@ -490,7 +511,8 @@ void knn_full_thread(int distance_type, int nq, int nb, int d, int k, const floa
         exit(1);
     }
     const int self_join = (b == v && nq == nb) ? 1 : 0;
-    int rc = search_rows_impl(nq, nb, d, k, b, v, self_join, 0, nq, assign, dis);
+    int rc = search_rows_impl(nq, nb, d, k, b, (size_t)d, v, (size_t)d, self_join, 0, nq, assign,
+                              dis);
     if (rc) {
         fprintf(stderr, "libpqh_knn: knn_full_thread failed: %s\n", g_err.c_str());
         exit(1);

@@ -36,6 +36,12 @@ int tc3_pick_nstage(const void *plan);
 cudaError_t launch_tc3(const void *maps, const void *args, int gcap, int n_items, int num_sms,
                        cudaStream_t stream);
 
+// ---- knn_tc5.cu (query operand in tensor memory) ----
+int tc5_tile_rows();
+int tc5_pick_nstage(const void *plan, int d16);
+cudaError_t launch_tc5(const void *maps, const void *args, const void *xh_q, const void *fold_a,
+                       int gcap, int d16, int n_items, int num_sms, cudaStream_t stream);
+
 // ---- knn_tcs.cu (streaming kernel for large d) ----
 cudaError_t launch_tcs(const void *maps, const void *args, int gcap, int d16, int n_items,
                        int num_sms, cudaStream_t stream);

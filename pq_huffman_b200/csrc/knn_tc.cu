@@ -245,21 +245,23 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     ptx::tc_fence_after_sync();
                     const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
                     const uint32_t a_base = ptx::smem_u32(smA);
-#pragma unroll 1
-                    for (int g = 0; g < 2; ++g) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + g * 128);
-                        uint32_t acc = 0;
-                        for (int s = 0; s < plan.nseg; ++s) {
-                            const TcSeg &sg = plan.seg[s];
-                            const uint32_t a_addr = a_base + sg.a_off + g * 128 * sg.bytes;
-                            const uint32_t b_addr = b_base + sg.b_off;
-                            const uint32_t sbo = 8 * sg.bytes, lay = seg_layout(sg.bytes);
-                            for (int kk = 0; kk < sg.bytes / 32; ++kk) {
-                                ptx::umma_f16(d_tmem, ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
-                                              ptx::make_smem_desc(b_addr + kk * 32, sbo, lay), idesc,
-                                              acc);
-                                acc = 1;
+                    // The two query tiles are independent accumulation chains: alternate
+                    // between them so that consecutive MMAs never depend on each other.
+                    uint32_t acc = 0;
+                    for (int s = 0; s < plan.nseg; ++s) {
+                        const TcSeg &sg = plan.seg[s];
+                        const uint32_t b_addr = b_base + sg.b_off;
+                        const uint32_t sbo = 8 * sg.bytes, lay = seg_layout(sg.bytes);
+                        for (int kk = 0; kk < sg.bytes / 32; ++kk) {
+                            const uint64_t bd = ptx::make_smem_desc(b_addr + kk * 32, sbo, lay);
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const uint32_t a_addr = a_base + sg.a_off + g * 128 * sg.bytes;
+                                ptx::umma_f16(tmem_base + (uint32_t)(as * 256 + g * 128),
+                                              ptx::make_smem_desc(a_addr + kk * 32, sbo, lay), bd,
+                                              idesc, acc);
                             }
+                            acc = 1;
                         }
                     }
                     ptx::umma_commit(&tail.b_empty[stage]);
@@ -869,7 +871,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int tc_variant() {
     const char *v = getenv("PQH_TC_VARIANT");
     const int x = v ? atoi(v) : 1;
-    return (x >= 1 && x <= 4) ? x : 1;
+    return (x >= 1 && x <= 5) ? x : 1;
 }
 
 // does the resident-A plan of `variant` fit in shared memory for this d16 / list capacity?
@@ -877,6 +879,7 @@ bool resident_fits(int variant, int d16, int gcap) {
     TcPlan p;
     if (!build_plan(d16, &p)) return false;
     if (variant == 3) return tc3_pick_nstage(&p) >= 2;
+    if (variant == 5) return tc5_pick_nstage(&p, d16) >= 3;
     size_t smem;
     if (variant == 2)
         smem = gcap == 128 ? tc2_smem_bytes<128>(p)
@@ -902,7 +905,7 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->gcap = pick_gcap(lo->L);
     lo->variant = tc_pick_variant(lo->d16, lo->gcap);
     lo->halves = 1;
-    const int bn = lo->variant == 2 ? 256 : TC_BN;
+    const int bn = lo->variant == 2 ? 256 : (lo->variant == 5 ? tc5_tile_rows() : TC_BN);
     const int units = lo->variant == 1 ? num_sms : num_sms / 2;
     const int qrows = lo->variant == 3 ? 512 : TC_ROWS;  // query rows per work item
     lo->n_qtiles = (n_rows + qrows - 1) / qrows;
@@ -1024,7 +1027,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     const uint64_t a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
     const uint32_t boxc[3] = {64, 32, 16};
     const uint32_t a_box_rows = lo.variant == 2 ? 128 : TC_ROWS;
-    const uint32_t b_box_rows = lo.variant == 3 ? 64 : TC_BN;
+    const uint32_t b_box_rows = lo.variant == 3 ? 64 : (lo.variant == 5 ? tc5_tile_rows() : TC_BN);
     for (int c = 0; c < 3; ++c) {
         // classes a small d never uses still need a legal box
         const uint32_t bc = boxc[c] <= (uint32_t)lo.d16 ? boxc[c] : 16;
@@ -1069,7 +1072,13 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             return e;                                                                            \
         KERNEL<<<(GRID), TC_THREADS, smem, stream>>>(maps, args);                                \
     } while (0)
-    if (lo.variant == 4) {
+    if (lo.variant == 5) {
+        args.nstage = tc5_pick_nstage(&args.plan, lo.d16);
+        if (args.nstage < 3) return cudaErrorInvalidValue;
+        if ((e = launch_tc5(&maps, &args, xh_q, fold_a, lo.gcap, lo.d16, n_items, num_sms,
+                            stream)) != cudaSuccess)
+            return e;
+    } else if (lo.variant == 4) {
         if ((e = launch_tcs(&maps, &args, lo.gcap, lo.d16, n_items, num_sms, stream)) != cudaSuccess)
             return e;
     } else if (lo.variant == 3) {

@@ -220,40 +220,42 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
 // list that reached its hard capacity.
 // tau_shared (pair kernel): ordered bits of the threshold shared by the two threads that
 // filter the two column halves of the same row.
-template <int GCAP, class Release>
-__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
+template <int GCAP, int NCOLS, class Release>
+__device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool special, int ib_hi,
                                             int self, int L, int lane, int debug_mode,
                                             uint32_t *tau_shared, float &tau, int &cnt,
                                             key64_t *list, unsigned (&ctr)[4], Release release,
                                             long long *tprof = nullptr) {
     const long long tp0 = tprof ? clock64() : 0;
+    static_assert(NCOLS == 128 || NCOLS == 80, "tile widths: 64 + 64 or 64 + 16 columns");
+    constexpr int NG = NCOLS / 8;  // groups of 8 columns
     unsigned groups = 0;
     {
-        uint32_t ra[64], rb[64];
+        uint32_t ra[64], rb[NCOLS - 64];
         ptx::tmem_ld_32x32b_x64(tbase, ra);
-        ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+        if constexpr (NCOLS == 128) ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+        else ptx::tmem_ld_32x32b_x16(tbase + 64, rb);
         ptx::tmem_wait_ld();
-        // 16 group maxima (groups of 8 columns), then the row maximum
-        float gm[16];
+        // group maxima (groups of 8 columns), then the row maximum
+        float gm[NG];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            uint32_t(&buf)[64] = (q < 8) ? ra : rb;
-            const int o = (q & 7) * 8;
-            float m = ptx::fmax3(__uint_as_float(buf[o]), __uint_as_float(buf[o + 1]),
-                                 __uint_as_float(buf[o + 2]));
-            m = ptx::fmax3(m, __uint_as_float(buf[o + 3]), __uint_as_float(buf[o + 4]));
-            m = ptx::fmax3(m, __uint_as_float(buf[o + 5]), __uint_as_float(buf[o + 6]));
-            gm[q] = fmaxf(m, __uint_as_float(buf[o + 7]));
+        for (int q = 0; q < NG; ++q) {
+            const uint32_t *buf = (q < 8) ? &ra[q * 8] : &rb[(q - 8) * 8];
+            float m = ptx::fmax3(__uint_as_float(buf[0]), __uint_as_float(buf[1]),
+                                 __uint_as_float(buf[2]));
+            m = ptx::fmax3(m, __uint_as_float(buf[3]), __uint_as_float(buf[4]));
+            m = ptx::fmax3(m, __uint_as_float(buf[5]), __uint_as_float(buf[6]));
+            gm[q] = fmaxf(m, __uint_as_float(buf[7]));
         }
-        float rm = ptx::fmax3(gm[0], gm[1], gm[2]);
+        float rm = gm[0];
 #pragma unroll
-        for (int q = 3; q < 15; q += 2) rm = ptx::fmax3(rm, gm[q], gm[q + 1]);
-        rm = fmaxf(rm, gm[15]);
+        for (int q = 1; q + 1 < NG; q += 2) rm = ptx::fmax3(rm, gm[q], gm[q + 1]);
+        if ((NG & 1) == 0) rm = fmaxf(rm, gm[NG - 1]);
         // common case: no row of the warp has anything above its threshold -> one vote, done
         if (__any_sync(0xffffffffu, rm > tau)) {
             unsigned gmask = 0;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
+            for (int q = 0; q < NG; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
             groups = __reduce_or_sync(0xffffffffu, gmask);
         }
     }
@@ -286,8 +288,8 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
     release();
     if (cnt > GCAP) __trap();  // list overflow would silently corrupt a neighbouring row's list
     const long long tp2 = tprof ? clock64() : 0;
-    // hard capacity: a tile can append up to TC_BN entries before this check runs again
-    unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - TC_BN);
+    // hard capacity: a tile can append up to NCOLS entries before this check runs again
+    unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - NCOLS);
 #pragma unroll 1
     while (need) {
         const int src = __ffs(need) - 1;
@@ -309,6 +311,16 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
         tprof[2] += tp2 - tp1;          // slow path up to the release
         tprof[3] += clock64() - tp2;    // hard shrinks
     }
+}
+
+template <int GCAP, class Release>
+__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
+                                            int self, int L, int lane, int debug_mode,
+                                            uint32_t *tau_shared, float &tau, int &cnt,
+                                            key64_t *list, unsigned (&ctr)[4], Release release,
+                                            long long *tprof = nullptr) {
+    filter_tile_n<GCAP, TC_BN>(tbase, col_base, special, ib_hi, self, L, lane, debug_mode,
+                               tau_shared, tau, cnt, list, ctr, release, tprof);
 }
 
 // While the tensor cores have not finished the next accumulator tile, use the idle time to

@@ -178,15 +178,16 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                         const uint32_t a_base = ptx::smem_u32(smem + stage * TS_STAGE_BYTES);
                         const uint32_t b_base = a_base + TS_A_BYTES;
                         const uint32_t sbo = 8 * bytes, lay = seg_layout(bytes);
-#pragma unroll 1
-                        for (int g = 0; g < 2; ++g) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + g * 128);
-                            const uint32_t a_addr = a_base + g * 128 * bytes;
-                            for (int kk = 0; kk < bytes / 32; ++kk)
-                                ptx::umma_f16(d_tmem,
-                                              ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
-                                              ptx::make_smem_desc(b_base + kk * 32, sbo, lay), idesc,
-                                              (i > 0 || kk > 0) ? 1u : 0u);
+                        // alternate between the two (independent) query tiles so that
+                        // consecutive MMAs never accumulate into the same tile
+                        for (int kk = 0; kk < bytes / 32; ++kk) {
+                            const uint64_t bd = ptx::make_smem_desc(b_base + kk * 32, sbo, lay);
+#pragma unroll
+                            for (int g = 0; g < 2; ++g)
+                                ptx::umma_f16(tmem_base + (uint32_t)(as * 256 + g * 128),
+                                              ptx::make_smem_desc(a_base + g * 128 * bytes + kk * 32,
+                                                                  sbo, lay),
+                                              bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
                         }
                         ptx::umma_commit(&tail.empty[stage]);
                         if (++stage == TS_NSTAGE) {

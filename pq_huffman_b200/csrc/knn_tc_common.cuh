@@ -270,13 +270,7 @@ __device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool
     }
     ++ctr[0];
     const int id_lim = special ? ib_hi : 0x7fffffff;
-#pragma unroll 1
-    do {
-        const int q = __ffs(groups) - 1;
-        groups &= groups - 1;
-        uint32_t v8[8];
-        ptx::tmem_ld_32x32b_x8(tbase + q * 8, v8);
-        ptx::tmem_wait_ld();
+    auto scan8 = [&](const uint32_t(&v8)[8], int q) {
         const int col0 = col_base + q * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -284,8 +278,32 @@ __device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool
             const bool p = (__uint_as_float(v8[j]) > tau) & (id < id_lim) & (id != self);
             append_if(p, list, cnt, v8[j], id);
         }
-    } while (groups != 0);
-    release();
+    };
+    const int q1 = __ffs(groups) - 1;
+    const unsigned rest = groups & (groups - 1);
+    if ((rest & (rest - 1)) == 0) {
+        // one or two flagged groups (the usual slow tile): fetch them, give the accumulator
+        // stage back, and only then scan -- the scan is off the tensor cores' critical path
+        const int q2 = rest ? __ffs(rest) - 1 : q1;
+        uint32_t va[8], vb[8];
+        ptx::tmem_ld_32x32b_x8(tbase + q1 * 8, va);
+        ptx::tmem_ld_32x32b_x8(tbase + q2 * 8, vb);
+        ptx::tmem_wait_ld();
+        release();
+        scan8(va, q1);
+        if (rest) scan8(vb, q2);
+    } else {
+#pragma unroll 1
+        do {
+            const int q = __ffs(groups) - 1;
+            groups &= groups - 1;
+            uint32_t v8[8];
+            ptx::tmem_ld_32x32b_x8(tbase + q * 8, v8);
+            ptx::tmem_wait_ld();
+            scan8(v8, q);
+        } while (groups != 0);
+        release();
+    }
     if (cnt > GCAP) __trap();  // list overflow would silently corrupt a neighbouring row's list
     const long long tp2 = tprof ? clock64() : 0;
     // hard capacity: a tile can append up to NCOLS entries before this check runs again

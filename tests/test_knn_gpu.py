@@ -169,6 +169,34 @@ def test_medium_property_100k():
         assert np.array_equal(a[r], ea[0]) and np.array_equal(d[r], ed[0])
 
 
+@pytest.mark.parametrize("n,d,k", [(2048, 128, 17), (2049, 128, 17), (2175, 64, 9), (4097, 128, 2),
+                                   (3000, 1, 4), (3000, 128, 34), (3000, 40, 100)])
+def test_tensor_path_boundaries(oracle, n, d, k):
+    """Sizes around the tensor-core path's limits: the smallest base it takes (2048), ragged last
+    tiles with the row's own column inside them, k = 2, d = 1, the largest k it takes (33 ->
+    kcap 32) and the first k it leaves to the exact kernel (34), and a large k."""
+    x = synth.sift_like(n, d, seed=3 * n + k)
+    got = knn.knn_full_thread(x, None, k)
+    st = knn.last_stats()
+    assert st["rows_tensor"] + st["rows_exact"] >= n
+    if k <= 33:
+        assert st["rows_tensor"] > 0
+    else:
+        assert st["rows_tensor"] == 0
+    assert_rows_equal(got, oracle.knn(x, None, k))
+
+
+def test_distinct_queries_ragged_through_tensor_path(oracle):
+    b = synth.gist_like(5001, 72, seed=8)
+    v = synth.gist_like(777, 72, seed=9)
+    got = knn.knn_full_thread(b, v, 12)
+    assert knn.last_stats()["rows_tensor"] > 0
+    assert_rows_equal(got, oracle.knn(b, v, 12))
+    a, d = knn.search_rows(b, v, 12, 100, 613)
+    full = oracle.knn(b, v, 12)
+    assert_rows_equal((a, d), (full[0][100:613], full[1][100:613]))
+
+
 def _n_devices():
     import torch
     return torch.cuda.device_count()

@@ -65,6 +65,29 @@ __device__ __forceinline__ void warp_sort_keys(key64_t *s, int n, int lane) {
     }
 }
 
+// Same, sized at run time: sorts the first `npow2` slots (a power of two >= n, >= 32), so a row
+// with few keys does not pay for the capacity of the buffer.
+__device__ __forceinline__ void warp_sort_keys_n(key64_t *s, int n, int lane) {
+    int npow2 = 32;
+    while (npow2 < n) npow2 <<= 1;
+    for (int i = n + lane; i < npow2; i += 32) s[i] = KEY_INF;
+    __syncwarp();
+#pragma unroll 1
+    for (int size = 2; size <= npow2; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < npow2 / 2; t += 32) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                key64_t a = s[lo], b = s[hi];
+                if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // number of elements of sorted a[0..n) that are < x
 __device__ __forceinline__ int lower_bound_keys(const key64_t *a, int n, key64_t x) {
     int lo = 0, hi = n;

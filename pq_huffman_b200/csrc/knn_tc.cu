@@ -169,7 +169,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = tail.tmem_base;
 
-    const int n_items = args.n_qtiles * args.nsplit;
+    const int n_items = total_items(args);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -177,10 +177,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             int stage = 0, it_par = 0, my_next = 0;
             uint32_t ph = 0, a_ph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int qt = item / args.nsplit, sp = item % args.nsplit;
-                int t_lo = sp * args.tiles_per_split;
-                int t_hi = t_lo + args.tiles_per_split;
-                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                const ItemInfo it = decode_item(args, item);
+                const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
                 ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
                 const int t0 = item_start_tile(args.sc, t_lo, t_hi, my_next);
                 my_next = t0;  // a full sweep ends where it started
@@ -228,10 +226,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             long long mma_wait_b = 0, mma_wait_acc = 0;
             const long long mma_t0 = clock64();
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int sp = item % args.nsplit;
-                int t_lo = sp * args.tiles_per_split;
-                int t_hi = t_lo + args.tiles_per_split;
-                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                const ItemInfo it = decode_item(args, item);
+                const int t_lo = it.t_lo, t_hi = it.t_hi;
                 ptx::mbar_wait(&tail.a_full, a_ph);
                 a_ph ^= 1;
                 for (int i = 0; i < t_hi - t_lo; ++i) {
@@ -296,14 +292,13 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         int it_par = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int qt = item / args.nsplit, sp = item % args.nsplit;
-            int t_lo = sp * args.tiles_per_split;
-            int t_hi = t_lo + args.tiles_per_split;
-            if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+            const ItemInfo it = decode_item(args, item);
+            const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
             const int r = qt * TC_ROWS + row_in_cta;
             const bool valid = r < args.n_rows;
             const int self = (valid && args.self_join) ? args.q_begin + r : -1;
-            const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
+            const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
+                                      : 0;
             key64_t *list = args.cand + slot * GCAP;
             float tau = valid ? NEG_INF : POS_INF;
             int cnt = 0;
@@ -611,7 +606,8 @@ struct RerankArgs {
     int q_begin;           // absolute query index of row 0 (self-join id, output naming)
     int out_q_begin;       // output row = q - out_q_begin
     int n_rows, nb, d, k, kcap, self_join;
-    int nlists, gcap;  // candidate lists per row (base splits x column halves)
+    int nlists, gcap;  // candidate lists per row (base splits), rows before the tail
+    int tail_row0, ns_tail;  // rows >= tail_row0 own ns_tail lists (knn_tc_common.cuh list_slot)
     const key64_t *cand;
     const int *cand_cnt;
     const float *cand_tau;
@@ -640,8 +636,9 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
     // gather the candidate ids of all splits; tau = max over splits
     int n = 0;
     float tau = __int_as_float(0xff800000);
-    for (int s = 0; s < a.nlists; ++s) {
-        const size_t slot = (size_t)r * a.nlists + s;
+    const int my_lists = r < a.tail_row0 ? a.nlists : a.ns_tail;
+    for (int s = 0; s < my_lists; ++s) {
+        const size_t slot = list_slot(r, s, a.tail_row0, a.nlists, a.ns_tail);
         const int c = a.cand_cnt[slot];
         const key64_t *l = a.cand + slot * a.gcap;
         for (int i = lane; i < c; i += 32) keys[n + i] = __ldcg(l + i);
@@ -708,7 +705,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         keys[i] = make_key(acc, id);
     }
     __syncwarp();
-    warp_sort_keys<NMAX>(keys, n, lane);
+    warp_sort_keys_n(keys, n, lane);  // n <= NMAX, NMAX a power of two
 
     // certificate: every non-candidate j has S'_j <= tau, hence
     //   true dist_j >= |x|^2 - 2 (tau + eps) / sigma^2   and the oracle's FP32 value
@@ -859,7 +856,9 @@ size_t tc_smem_bytes(const TcPlan &p) {
 struct TcLayout {
     size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
     int d16, L, L_exact, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
-    int variant, halves, nlists;  // variant 2 = CTA-pair kernel (two column halves per row)
+    int variant, halves, nlists;
+    int q_tail0, ns_tail, tiles_per_split_tail, qrows;  // tail of the work list (TcArgs)
+    size_t n_slots;                                      // candidate lists in all
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -926,6 +925,30 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->nsplit = nsplit;
     lo->nlists = nsplit * lo->halves;
     lo->tiles_per_split = (lo->n_btiles + nsplit - 1) / nsplit;
+    // The last round of the persistent grid: if the query tiles left over after the full rounds
+    // occupy at most half of the SMs, cut each of them into 2..4 base splits so the round
+    // finishes in a fraction of an item time (8 GPUs x 125k rows: 489 tiles = 3 rounds + 45).
+    lo->qrows = qrows;
+    lo->q_tail0 = lo->n_qtiles;
+    lo->ns_tail = 1;
+    lo->tiles_per_split_tail = lo->n_btiles;
+    if ((lo->variant == 1 || lo->variant == 4) && nsplit == 1 && lo->n_qtiles > units &&
+        !getenv("PQH_TC_NO_TAIL")) {
+        const int rem = lo->n_qtiles % units;
+        int ns = rem > 0 ? units / rem : 1;
+        if (ns > 4) ns = 4;
+        while (ns > 1 && (ns > max_lists || lo->n_btiles / ns < 16)) --ns;
+        if (ns > 1) {
+            lo->q_tail0 = lo->n_qtiles - rem;
+            lo->ns_tail = ns;
+            lo->tiles_per_split_tail = (lo->n_btiles + ns - 1) / ns;
+        }
+    }
+    {
+        const long long tail_row0 = (long long)lo->q_tail0 * qrows;
+        const long long rows_main = tail_row0 < n_rows ? tail_row0 : n_rows;
+        lo->n_slots = (size_t)rows_main * lo->nlists + (size_t)(n_rows - rows_main) * lo->ns_tail;
+    }
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -939,9 +962,9 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->fold_a = take((size_t)TC_ROWS * FOLD_COLS * sizeof(__half));
     lo->norm_b = take((size_t)nb * sizeof(double));
     lo->norm_q = self_join ? lo->norm_b : take((size_t)nq_src_rows * sizeof(double));
-    lo->cand = take((size_t)n_rows * lo->nlists * lo->gcap * sizeof(key64_t));
-    lo->cnt = take((size_t)n_rows * lo->nlists * sizeof(int));
-    lo->tau = take((size_t)n_rows * lo->nlists * sizeof(float));
+    lo->cand = take(lo->n_slots * lo->gcap * sizeof(key64_t));
+    lo->cnt = take(lo->n_slots * sizeof(int));
+    lo->tau = take(lo->n_slots * sizeof(float));
     lo->fb_rows = take((size_t)n_rows * sizeof(int));
     lo->total = off + 1024;
 }
@@ -1046,6 +1069,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     args.self_join = self_join;
     args.n_qtiles = lo.n_qtiles;
     args.nsplit = lo.nsplit;
+    args.q_tail0 = lo.q_tail0;
+    args.ns_tail = lo.ns_tail;
+    args.tiles_per_split_tail = lo.tiles_per_split_tail;
     args.tiles_per_split = lo.tiles_per_split;
     args.n_btiles = lo.n_btiles;
     {
@@ -1061,7 +1087,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     args.cand_cnt = cnt;
     args.cand_tau = tau;
 
-    const int n_items = lo.n_qtiles * lo.nsplit;
+    const int n_items = lo.q_tail0 * lo.nsplit + (lo.n_qtiles - lo.q_tail0) * lo.ns_tail;
     size_t smem;
     if (ev) cudaEventRecord(ev[1], stream);
 #define LAUNCH_TC(KERNEL, SMEM, GRID)                                                            \
@@ -1117,6 +1143,8 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     ra.kcap = kcap;
     ra.self_join = self_join;
     ra.nlists = lo.nlists;
+    ra.tail_row0 = lo.q_tail0 * lo.qrows;
+    ra.ns_tail = lo.ns_tail;
     ra.gcap = lo.gcap;
     ra.cand = cand;
     ra.cand_cnt = cnt;
@@ -1130,7 +1158,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     ra.dis = d_dis;
     ra.fb_rows = fb_rows;
     ra.fb_count = &sc->fb_count;
-    const int nmax = lo.gcap * lo.nlists;
+    const int nmax = lo.gcap * (lo.nlists > lo.ns_tail ? lo.nlists : lo.ns_tail);
     const int rgrid = (n_rows + RR_WARPS - 1) / RR_WARPS;
     const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
 #define LAUNCH_RR(N)                                                                             \

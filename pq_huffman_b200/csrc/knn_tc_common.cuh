@@ -50,6 +50,10 @@ struct TcArgs {
     int nb;
     int self_join;
     int n_qtiles, nsplit, tiles_per_split, n_btiles;
+    // Tail of the work list: the last n_qtiles - q_tail0 query tiles (the partly filled last
+    // round of the persistent grid) are cut into ns_tail base splits each so that every SM gets
+    // a piece; their rows own ns_tail candidate lists instead of nsplit.
+    int q_tail0, ns_tail, tiles_per_split_tail;
     int kcap;        // neighbours needed per row (k, or k-1 for a self-join)
     int nstage;      // pair kernel: depth of the B-tile ring
     int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
@@ -67,6 +71,38 @@ struct TcMaps {
     CUtensorMap fa;    // fold constants [256 x 16]
     CUtensorMap fb;    // fold pieces    [nb x 16]
 };
+
+struct ItemInfo {
+    int qt, sp, t_lo, t_hi;
+};
+__device__ __forceinline__ int total_items(const TcArgs &a) {
+    return a.q_tail0 * a.nsplit + (a.n_qtiles - a.q_tail0) * a.ns_tail;
+}
+__device__ __forceinline__ ItemInfo decode_item(const TcArgs &a, int item) {
+    ItemInfo it;
+    const int n_main = a.q_tail0 * a.nsplit;
+    int tps;
+    if (item < n_main) {
+        it.qt = item / a.nsplit;
+        it.sp = item % a.nsplit;
+        tps = a.tiles_per_split;
+    } else {
+        const int j = item - n_main;
+        it.qt = a.q_tail0 + j / a.ns_tail;
+        it.sp = j % a.ns_tail;
+        tps = a.tiles_per_split_tail;
+    }
+    it.t_lo = it.sp * tps;
+    it.t_hi = it.t_lo + tps;
+    if (it.t_hi > a.n_btiles) it.t_hi = a.n_btiles;
+    return it;
+}
+// candidate-list slot of (query row r of this launch, base split sp)
+__host__ __device__ __forceinline__ size_t list_slot(int r, int sp, int tail_row0, int nsplit,
+                                                      int ns_tail) {
+    return r < tail_row0 ? (size_t)r * nsplit + sp
+                         : (size_t)tail_row0 * nsplit + (size_t)(r - tail_row0) * ns_tail + sp;
+}
 
 // Base-tile order of one work item.  Every CTA sweeps ALL tiles of its range, so the order is
 // free: CTA 0 never restarts -- it keeps cycling through the tiles and publishes its position --

@@ -110,7 +110,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = tail.tmem_base;
 
-    const int n_items = args.n_qtiles * args.nsplit;
+    const int n_items = total_items(args);
 
     if (warp == 0) {
         // ===================== TMA producer: one K-block of A and B per stage =============
@@ -118,10 +118,8 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
             int stage = 0, it_par = 0, my_next = 0;
             uint32_t ph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int qt = item / args.nsplit, sp = item % args.nsplit;
-                int t_lo = sp * args.tiles_per_split;
-                int t_hi = t_lo + args.tiles_per_split;
-                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                const ItemInfo it = decode_item(args, item);
+                const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
                 const int arow = args.q_op_begin + qt * TC_ROWS;
                 // the slot of item i is reused by item i+2; the producer is at most one ring
                 // (a fraction of a tile) ahead of the MMA, the epilogue at most two tiles behind
@@ -163,10 +161,8 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
             int stage = 0, as = 0;
             uint32_t ph = 0, acc_ph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int sp = item % args.nsplit;
-                int t_lo = sp * args.tiles_per_split;
-                int t_hi = t_lo + args.tiles_per_split;
-                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+                const ItemInfo it = decode_item(args, item);
+                const int t_lo = it.t_lo, t_hi = it.t_hi;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {
                     ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
                     ptx::tc_fence_after_sync();
@@ -215,14 +211,13 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
         int it_par = 0;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int qt = item / args.nsplit, sp = item % args.nsplit;
-            int t_lo = sp * args.tiles_per_split;
-            int t_hi = t_lo + args.tiles_per_split;
-            if (t_hi > args.n_btiles) t_hi = args.n_btiles;
+            const ItemInfo it = decode_item(args, item);
+            const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
             const int r = qt * TC_ROWS + row_in_cta;
             const bool valid = r < args.n_rows;
             const int self = (valid && args.self_join) ? args.q_begin + r : -1;
-            const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
+            const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
+                                      : 0;
             key64_t *list = args.cand + slot * GCAP;
             float tau = valid ? NEG_INF : POS_INF;
             int cnt = 0;

@@ -825,8 +825,8 @@ bool build_plan(int d16, TcPlan *p) {
     return true;
 }
 
-// candidates kept per row: 4x the neighbours asked for when the FP16 operands are rounded
-// (slack for the certificate), 2x when they are exact (integer-valued data)
+// candidates kept per row (slack for the certificate): ~1.5x the neighbours asked for when the
+// FP16 operands are exact (integer-valued data), max(64, 2x) when they are rounded
 int pick_L(int kcap, bool inexact) {
     if (!inexact) {
         // exact operands: the certificate only has to absorb the accumulation bound, a
@@ -835,9 +835,13 @@ int pick_L(int kcap, bool inexact) {
         if (e) return atoi(e);
         return (kcap + kcap / 2 + 7) / 8 * 8;
     }
-    int L = 4 * kcap;
+    if (const char *e = getenv("PQH_TC_LINEXACT")) return atoi(e);
+    // rounded operands: 64 candidates, or twice the neighbours asked for if that is more.
+    // Measured (profiles/README.md): GIST-shaped k=16 needs 64 (at 32, 10 % of the rows fail the
+    // certificate); Deep-shaped k=32 certifies every row at 64 and runs 1.5x faster than at 128.
+    int L = 2 * kcap;
     L = (L + 31) / 32 * 32;
-    if (L < 32) L = 32;
+    if (L < 64) L = 64;
     return L;
 }
 // list capacity: the filter checks it once per tile, after up to TC_BN (128) appends

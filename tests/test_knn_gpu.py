@@ -186,6 +186,20 @@ def test_tensor_path_boundaries(oracle, n, d, k):
     assert_rows_equal(got, oracle.knn(x, None, k))
 
 
+def test_mass_duplicates_through_tensor_path(oracle):
+    """2500 copies of one vector: far more exact ties than the candidate lists hold, so the
+    certificate cannot accept those rows (a non-candidate is exactly as close as the k-th
+    neighbour) and the exact kernel has to order them by position."""
+    rng = np.random.default_rng(3)
+    one = synth.sift_like(1, 48, seed=2)
+    x = np.concatenate([np.tile(one, (2500, 1)), synth.sift_like(700, 48, seed=5)])
+    x = np.ascontiguousarray(x[rng.permutation(len(x))])
+    got = knn.knn_full_thread(x, None, 9)
+    st = knn.last_stats()
+    assert st["rows_exact"] >= 2500
+    assert_rows_equal(got, oracle.knn(x, None, 9))
+
+
 def test_distinct_queries_ragged_through_tensor_path(oracle):
     b = synth.gist_like(5001, 72, seed=8)
     v = synth.gist_like(777, 72, seed=9)

@@ -977,7 +977,7 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
 
 bool tc_supported(int n_rows, int nb, int d, int k, int self_join) {
     const int kcap = self_join ? k - 1 : k;
-    if (kcap < 1 || kcap > 32) return false;
+    if (kcap < 1 || kcap > 64) return false;  // list capacity 512 holds L = 128 candidates
     if (nb < 2048 || n_rows < 1) return false;
     if (d < 1 || d > 4096) return false;
     return true;  // the streaming kernel takes every d the resident kernels cannot

@@ -170,16 +170,16 @@ def test_medium_property_100k():
 
 
 @pytest.mark.parametrize("n,d,k", [(2048, 128, 17), (2049, 128, 17), (2175, 64, 9), (4097, 128, 2),
-                                   (3000, 1, 4), (3000, 128, 34), (3000, 40, 100)])
+                                   (3000, 1, 4), (3000, 128, 34), (3000, 64, 65), (3000, 64, 66), (3000, 40, 100)])
 def test_tensor_path_boundaries(oracle, n, d, k):
     """Sizes around the tensor-core path's limits: the smallest base it takes (2048), ragged last
-    tiles with the row's own column inside them, k = 2, d = 1, the largest k it takes (33 ->
-    kcap 32) and the first k it leaves to the exact kernel (34), and a large k."""
+    tiles with the row's own column inside them, k = 2, d = 1, the largest k it takes (65 ->
+    kcap 64) and the first k it leaves to the exact kernel (66), and a large k."""
     x = synth.sift_like(n, d, seed=3 * n + k)
     got = knn.knn_full_thread(x, None, k)
     st = knn.last_stats()
     assert st["rows_tensor"] + st["rows_exact"] >= n
-    if k <= 33:
+    if k <= 65:
         assert st["rows_tensor"] > 0
     else:
         assert st["rows_tensor"] == 0

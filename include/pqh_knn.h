@@ -130,6 +130,8 @@ typedef struct pqh_knn_stats {
     long long rows;            /* query rows searched */
     long long rows_tensor;     /* rows resolved by the tensor-core pass + certificate */
     long long rows_exact;      /* rows (re)done by the exact FP32 kernel */
+    long long rows_second_pass;/* rows whose first certificate failed and that were redone by a
+                                  second tensor-core pass with longer candidate lists */
     long long launches;        /* kernels launched */
     double ms_total;           /* wall time of the call, host clock */
     double ms_h2d, ms_kernels, ms_d2h; /* device-event times of the phases */

@@ -28,6 +28,7 @@ class Stats(C.Structure):
         ("rows", C.c_longlong),
         ("rows_tensor", C.c_longlong),
         ("rows_exact", C.c_longlong),
+        ("rows_second_pass", C.c_longlong),
         ("launches", C.c_longlong),
         ("ms_total", C.c_double),
         ("ms_h2d", C.c_double),

@@ -21,6 +21,7 @@ struct TcTimes {
     float ms_prep = 0.f, ms_gemm = 0.f, ms_rerank = 0.f;
     double candidates = 0.0;
     int inexact = 0;
+    long long rows_pass2 = 0;   // rows redone by the second tensor-core pass
     float eps_ratio_max = 0.f;  // PQH_TC_CHECK_EPS: max |S'_tensor - S'_fp64| / eps
 };
 bool tc_supported(int n_rows, int nb, int d, int k, int self_join);

@@ -106,6 +106,18 @@ prep_rows_kernel(const float *__restrict__ x, int n, int d, int d16, __half *__r
     }
 }
 
+// second pass: collect the query vectors of the rows that failed the first certificate
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float *__restrict__ src, int src_row0, const int *__restrict__ ids, int n,
+                   int d, float *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float *s = src + (size_t)(ids[row] - src_row0) * d;
+    float *o = dst + (size_t)row * d;
+    for (int i = lane; i < d; i += 32) o[i] = s[i];
+}
+
 __global__ void fold_const_kernel(__half *__restrict__ fa) {
     // [256 x 16]: every query row multiplies the base pieces by (4096, 2, 2^-10)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,7 +308,9 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
             const int r = qt * TC_ROWS + row_in_cta;
             const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const int self = (valid && args.self_join)
+                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
+                                 : -1;
             const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
                                       : 0;
             key64_t *list = args.cand + slot * GCAP;
@@ -544,7 +558,9 @@ knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             if (t_hi > args.n_btiles) t_hi = args.n_btiles;
             const int r = qt * TC_ROWS + (int)rank * 128 + row_in_cta;
             const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const int self = (valid && args.self_join)
+                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
+                                 : -1;
             const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
             key64_t *list = args.cand + slot * GCAP;
             float tau = valid ? NEG_INF : POS_INF;
@@ -604,6 +620,7 @@ struct RerankArgs {
     const float *queries;  // row r of this launch is queries[(q_row_begin + r) * d]
     int q_row_begin;
     int q_begin;           // absolute query index of row 0 (self-join id, output naming)
+    const int *row_ids;    // second pass: absolute query index of every row instead
     int out_q_begin;       // output row = q - out_q_begin
     int n_rows, nb, d, k, kcap, self_join;
     int nlists, gcap;  // candidate lists per row (base splits), rows before the tail
@@ -631,7 +648,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
                   (size_t)warp * a.d;
     const int r = blockIdx.x * RR_WARPS + warp;
     if (r >= a.n_rows) return;
-    const int q = a.q_begin + r;
+    const int q = a.row_ids ? a.row_ids[r] : a.q_begin + r;
 
     // gather the candidate ids of all splits; tau = max over splits
     int n = 0;
@@ -859,6 +876,9 @@ size_t tc_smem_bytes(const TcPlan &p) {
 
 struct TcLayout {
     size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
+    // second pass (rows that failed the first certificate, redone with longer lists)
+    size_t p2_q, p2_xh, p2_norm, p2_cand, p2_cnt, p2_tau, p2_fb;
+    int p2_rows;  // rows per second-pass batch
     int d16, L, L_exact, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
     int variant, halves, nlists;
     int q_tail0, ns_tail, tiles_per_split_tail, qrows;  // tail of the work list (TcArgs)
@@ -899,13 +919,15 @@ int tc_pick_variant(int d16, int gcap) {
     return v;
 }
 
+constexpr int P2_GCAP = 512, P2_MAX_LISTS = 4;
+
 void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join, int num_sms,
-               TcLayout *lo) {
+               TcLayout *lo, int L_override = 0) {
     const int kcap = self_join ? k - 1 : k;
     lo->d16 = (d + 15) / 16 * 16;
-    lo->L = pick_L(kcap, true);
-    lo->L_exact = pick_L(kcap, false);
-    lo->gcap = pick_gcap(lo->L);
+    lo->L = L_override ? L_override : pick_L(kcap, true);
+    lo->L_exact = L_override ? L_override : pick_L(kcap, false);
+    lo->gcap = L_override ? P2_GCAP : pick_gcap(lo->L);
     lo->variant = tc_pick_variant(lo->d16, lo->gcap);
     lo->halves = 1;
     const int bn = lo->variant == 2 ? 256 : (lo->variant == 5 ? tc5_tile_rows() : TC_BN);
@@ -970,6 +992,19 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->cnt = take(lo->n_slots * sizeof(int));
     lo->tau = take(lo->n_slots * sizeof(float));
     lo->fb_rows = take((size_t)n_rows * sizeof(int));
+    {
+        int p2 = n_rows / 16;
+        if (p2 < 2048) p2 = 2048;
+        if (p2 > n_rows) p2 = n_rows;
+        lo->p2_rows = p2;
+        lo->p2_q = take((size_t)p2 * d * sizeof(float));
+        lo->p2_xh = take((size_t)p2 * lo->d16 * sizeof(__half));
+        lo->p2_norm = take((size_t)p2 * sizeof(double));
+        lo->p2_cand = take((size_t)p2 * P2_MAX_LISTS * P2_GCAP * sizeof(key64_t));
+        lo->p2_cnt = take((size_t)p2 * P2_MAX_LISTS * sizeof(int));
+        lo->p2_tau = take((size_t)p2 * P2_MAX_LISTS * sizeof(float));
+        lo->p2_fb = take((size_t)n_rows * sizeof(int));
+    }
     lo->total = off + 1024;
 }
 
@@ -1047,141 +1082,178 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
     ++*launches;
 
-    // ---- tensor maps + plan ----
-    TcMaps maps;
-    TcArgs args;
-    if (!build_plan(lo.d16, &args.plan) && lo.variant != 4) return cudaErrorInvalidValue;
-    const uint64_t a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
-    const uint32_t boxc[3] = {64, 32, 16};
-    const uint32_t a_box_rows = lo.variant == 2 ? 128 : TC_ROWS;
-    const uint32_t b_box_rows = lo.variant == 3 ? 64 : (lo.variant == 5 ? tc5_tile_rows() : TC_BN);
-    for (int c = 0; c < 3; ++c) {
-        // classes a small d never uses still need a legal box
-        const uint32_t bc = boxc[c] <= (uint32_t)lo.d16 ? boxc[c] : 16;
-        if (!make_map(&maps.a[c], xh_q, a_rows, lo.d16, bc, a_box_rows) ||
-            !make_map(&maps.b[c], xh_b, nb, lo.d16, bc, b_box_rows))
+    // ---- one pass = tensor-core kernel + re-rank over a set of query rows ----
+    struct Pass {
+        const TcLayout *lo;      // geometry (tiles, splits, list sizes) of this pass
+        const __half *xh_q;      // FP16 operand whose row (q_op_begin + r) is query r
+        uint64_t a_rows;         // rows of that operand
+        int q_op_begin;
+        const float *q_mat;      // FP32 matrix whose row (q_row_begin + r) is query r
+        int q_row_begin;
+        const double *qnorm64;   // indexed like q_mat
+        const int *row_ids;      // absolute query ids (second pass) or null
+        int n_rows;
+        key64_t *cand;
+        int *cnt;
+        float *tau;
+        int *fb_rows;
+        uint32_t *fb_count;
+    };
+    const char *dbg_env = getenv("PQH_TC_DEBUG");
+    const int debug_mode = dbg_env ? atoi(dbg_env) : 0;
+    auto run_pass = [&](const Pass &p) -> cudaError_t {
+        const TcLayout &pl = *p.lo;
+        TcMaps maps;
+        TcArgs args;
+        if (!build_plan(pl.d16, &args.plan) && pl.variant != 4) return cudaErrorInvalidValue;
+        const uint32_t boxc[3] = {64, 32, 16};
+        const uint32_t a_box_rows = pl.variant == 2 ? 128 : TC_ROWS;
+        const uint32_t b_box_rows =
+            pl.variant == 3 ? 64 : (pl.variant == 5 ? tc5_tile_rows() : TC_BN);
+        for (int c = 0; c < 3; ++c) {
+            // classes a small d never uses still need a legal box
+            const uint32_t bc = boxc[c] <= (uint32_t)pl.d16 ? boxc[c] : 16;
+            if (!make_map(&maps.a[c], p.xh_q, p.a_rows, pl.d16, bc, a_box_rows) ||
+                !make_map(&maps.b[c], xh_b, nb, pl.d16, bc, b_box_rows))
+                return cudaErrorInvalidValue;
+        }
+        if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, a_box_rows) ||
+            !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, b_box_rows))
             return cudaErrorInvalidValue;
-    }
-    if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, a_box_rows) ||
-        !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, b_box_rows))
-        return cudaErrorInvalidValue;
 
-    args.n_rows = n_rows;
-    args.q_begin = q_begin;
-    args.q_op_begin = self_join ? q_begin : 0;
-    args.nb = nb;
-    args.self_join = self_join;
-    args.n_qtiles = lo.n_qtiles;
-    args.nsplit = lo.nsplit;
-    args.q_tail0 = lo.q_tail0;
-    args.ns_tail = lo.ns_tail;
-    args.tiles_per_split_tail = lo.tiles_per_split_tail;
-    args.tiles_per_split = lo.tiles_per_split;
-    args.n_btiles = lo.n_btiles;
-    {
-        const char *dbg = getenv("PQH_TC_DEBUG");
-        args.debug_mode = dbg ? atoi(dbg) : 0;
-    }
-    args.nstage = 0;
-    args.kcap = kcap;
-    args.L_exact = lo.L_exact;
-    args.L_inexact = lo.L;
-    args.sc = sc;
-    args.cand = cand;
-    args.cand_cnt = cnt;
-    args.cand_tau = tau;
+        args.n_rows = p.n_rows;
+        args.q_begin = q_begin;
+        args.q_op_begin = p.q_op_begin;
+        args.nb = nb;
+        args.self_join = self_join;
+        args.row_ids = p.row_ids;
+        args.n_qtiles = pl.n_qtiles;
+        args.nsplit = pl.nsplit;
+        args.q_tail0 = pl.q_tail0;
+        args.ns_tail = pl.ns_tail;
+        args.tiles_per_split_tail = pl.tiles_per_split_tail;
+        args.tiles_per_split = pl.tiles_per_split;
+        args.n_btiles = pl.n_btiles;
+        args.debug_mode = debug_mode;
+        args.nstage = 0;
+        args.kcap = kcap;
+        args.L_exact = pl.L_exact;
+        args.L_inexact = pl.L;
+        args.sc = sc;
+        args.cand = p.cand;
+        args.cand_cnt = p.cnt;
+        args.cand_tau = p.tau;
 
-    const int n_items = lo.q_tail0 * lo.nsplit + (lo.n_qtiles - lo.q_tail0) * lo.ns_tail;
-    size_t smem;
-    if (ev) cudaEventRecord(ev[1], stream);
+        const int n_items = pl.q_tail0 * pl.nsplit + (pl.n_qtiles - pl.q_tail0) * pl.ns_tail;
+        size_t smem;
+        cudaError_t pe;
 #define LAUNCH_TC(KERNEL, SMEM, GRID)                                                            \
     do {                                                                                         \
         smem = (SMEM);                                                                           \
-        if ((e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                      (int)smem)) != cudaSuccess)                                \
-            return e;                                                                            \
+        if ((pe = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                       (int)smem)) != cudaSuccess)                               \
+            return pe;                                                                           \
         KERNEL<<<(GRID), TC_THREADS, smem, stream>>>(maps, args);                                \
     } while (0)
-    if (lo.variant == 5) {
-        args.nstage = tc5_pick_nstage(&args.plan, lo.d16);
-        if (args.nstage < 3) return cudaErrorInvalidValue;
-        if ((e = launch_tc5(&maps, &args, xh_q, fold_a, lo.gcap, lo.d16, n_items, num_sms,
-                            stream)) != cudaSuccess)
-            return e;
-    } else if (lo.variant == 4) {
-        if ((e = launch_tcs(&maps, &args, lo.gcap, lo.d16, n_items, num_sms, stream)) != cudaSuccess)
-            return e;
-    } else if (lo.variant == 3) {
-        args.nstage = tc3_pick_nstage(&args.plan);
-        if (args.nstage < 2) return cudaErrorInvalidValue;
-        if ((e = launch_tc3(&maps, &args, lo.gcap, n_items, num_sms, stream)) != cudaSuccess)
-            return e;
-    } else if (lo.variant == 2) {
-        const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
-        const int grid = 2 * clusters;
-        if (lo.gcap == 128) LAUNCH_TC(knn_tc2_kernel<128>, tc2_smem_bytes<128>(args.plan), grid);
-        else if (lo.gcap == 256) LAUNCH_TC(knn_tc2_kernel<256>, tc2_smem_bytes<256>(args.plan), grid);
-        else LAUNCH_TC(knn_tc2_kernel<512>, tc2_smem_bytes<512>(args.plan), grid);
-    } else {
-        const int grid = n_items < num_sms ? n_items : num_sms;
-        if (lo.gcap == 128) LAUNCH_TC(knn_tc_kernel<128>, tc_smem_bytes<128>(args.plan), grid);
-        else if (lo.gcap == 256) LAUNCH_TC(knn_tc_kernel<256>, tc_smem_bytes<256>(args.plan), grid);
-        else LAUNCH_TC(knn_tc_kernel<512>, tc_smem_bytes<512>(args.plan), grid);
-    }
+        if (pl.variant == 5) {
+            args.nstage = tc5_pick_nstage(&args.plan, pl.d16);
+            if (args.nstage < 3) return cudaErrorInvalidValue;
+            if ((pe = launch_tc5(&maps, &args, p.xh_q, fold_a, pl.gcap, pl.d16, n_items, num_sms,
+                                 stream)) != cudaSuccess)
+                return pe;
+        } else if (pl.variant == 4) {
+            if ((pe = launch_tcs(&maps, &args, pl.gcap, pl.d16, n_items, num_sms, stream)) !=
+                cudaSuccess)
+                return pe;
+        } else if (pl.variant == 3) {
+            args.nstage = tc3_pick_nstage(&args.plan);
+            if (args.nstage < 2) return cudaErrorInvalidValue;
+            if ((pe = launch_tc3(&maps, &args, pl.gcap, n_items, num_sms, stream)) != cudaSuccess)
+                return pe;
+        } else if (pl.variant == 2) {
+            const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
+            const int grid = 2 * clusters;
+            if (pl.gcap == 256) LAUNCH_TC(knn_tc2_kernel<256>, tc2_smem_bytes<256>(args.plan), grid);
+            else LAUNCH_TC(knn_tc2_kernel<512>, tc2_smem_bytes<512>(args.plan), grid);
+        } else {
+            const int grid = n_items < num_sms ? n_items : num_sms;
+            if (pl.gcap == 256) LAUNCH_TC(knn_tc_kernel<256>, tc_smem_bytes<256>(args.plan), grid);
+            else LAUNCH_TC(knn_tc_kernel<512>, tc_smem_bytes<512>(args.plan), grid);
+        }
 #undef LAUNCH_TC
-    ++*launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (ev) cudaEventRecord(ev[2], stream);
+        ++*launches;
+        if ((pe = cudaGetLastError()) != cudaSuccess) return pe;
+        if (ev && !p.row_ids) cudaEventRecord(ev[2], stream);
 
-    // ---- re-rank + certificate ----
-    RerankArgs ra;
-    ra.base = d_base;
-    ra.queries = self_join ? d_base : d_queries;
-    ra.q_row_begin = q_src0;
-    ra.q_begin = q_begin;
-    ra.out_q_begin = out_q_begin;
-    ra.n_rows = n_rows;
-    ra.nb = nb;
-    ra.d = d;
-    ra.k = k;
-    ra.kcap = kcap;
-    ra.self_join = self_join;
-    ra.nlists = lo.nlists;
-    ra.tail_row0 = lo.q_tail0 * lo.qrows;
-    ra.ns_tail = lo.ns_tail;
-    ra.gcap = lo.gcap;
-    ra.cand = cand;
-    ra.cand_cnt = cnt;
-    ra.cand_tau = tau;
-    ra.qnorm64 = self_join ? norm_b : norm_q - q_src0;  // indexed by q_row_begin + r
-    ra.bnorm64 = norm_b;
-    ra.check_eps = getenv("PQH_TC_CHECK_EPS") ? 1 : 0;
-    ra.sc = sc;
-    ra.ksteps = (lo.d16 + FOLD_COLS) / 16;
-    ra.assign = d_assign;
-    ra.dis = d_dis;
-    ra.fb_rows = fb_rows;
-    ra.fb_count = &sc->fb_count;
-    const int nmax = lo.gcap * (lo.nlists > lo.ns_tail ? lo.nlists : lo.ns_tail);
-    const int rgrid = (n_rows + RR_WARPS - 1) / RR_WARPS;
-    const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
+        // ---- re-rank + certificate ----
+        RerankArgs ra;
+        ra.base = d_base;
+        ra.queries = p.q_mat;
+        ra.q_row_begin = p.q_row_begin;
+        ra.q_begin = q_begin;
+        ra.row_ids = p.row_ids;
+        ra.out_q_begin = out_q_begin;
+        ra.n_rows = p.n_rows;
+        ra.nb = nb;
+        ra.d = d;
+        ra.k = k;
+        ra.kcap = kcap;
+        ra.self_join = self_join;
+        ra.nlists = pl.nlists;
+        ra.tail_row0 = pl.q_tail0 * pl.qrows;
+        ra.ns_tail = pl.ns_tail;
+        ra.gcap = pl.gcap;
+        ra.cand = p.cand;
+        ra.cand_cnt = p.cnt;
+        ra.cand_tau = p.tau;
+        ra.qnorm64 = p.qnorm64;
+        ra.bnorm64 = norm_b;
+        ra.check_eps = getenv("PQH_TC_CHECK_EPS") ? 1 : 0;
+        ra.sc = sc;
+        ra.ksteps = (pl.d16 + FOLD_COLS) / 16;
+        ra.assign = d_assign;
+        ra.dis = d_dis;
+        ra.fb_rows = p.fb_rows;
+        ra.fb_count = p.fb_count;
+        const int nmax = pl.gcap * (pl.nlists > pl.ns_tail ? pl.nlists : pl.ns_tail);
+        const int rgrid = (p.n_rows + RR_WARPS - 1) / RR_WARPS;
+        const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
 #define LAUNCH_RR(N)                                                                             \
     do {                                                                                         \
         size_t sm = (size_t)RR_WARPS * N * sizeof(key64_t) + qbytes;                             \
-        if ((e = cudaFuncSetAttribute(knn_rerank_kernel<N>,                                      \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) !=  \
+        if ((pe = cudaFuncSetAttribute(knn_rerank_kernel<N>,                                     \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != \
             cudaSuccess)                                                                         \
-            return e;                                                                            \
+            return pe;                                                                           \
         knn_rerank_kernel<N><<<rgrid, RR_WARPS * 32, sm, stream>>>(ra);                          \
     } while (0)
-    if (nmax <= 128) LAUNCH_RR(128);
-    else if (nmax <= 256) LAUNCH_RR(256);
-    else if (nmax <= 512) LAUNCH_RR(512);
-    else if (nmax <= 1024) LAUNCH_RR(1024);
-    else LAUNCH_RR(2048);
+        if (nmax <= 256) LAUNCH_RR(256);
+        else if (nmax <= 512) LAUNCH_RR(512);
+        else if (nmax <= 1024) LAUNCH_RR(1024);
+        else LAUNCH_RR(2048);
 #undef LAUNCH_RR
-    ++*launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++*launches;
+        return cudaGetLastError();
+    };
+
+    // ---- first pass: every row of this launch ----
+    if (ev) cudaEventRecord(ev[1], stream);
+    Pass p1;
+    p1.lo = &lo;
+    p1.xh_q = xh_q;
+    p1.a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
+    p1.q_op_begin = self_join ? q_begin : 0;
+    p1.q_mat = self_join ? d_base : d_queries;
+    p1.q_row_begin = q_src0;
+    p1.qnorm64 = self_join ? norm_b : norm_q - q_src0;  // indexed by q_row_begin + r
+    p1.row_ids = nullptr;
+    p1.n_rows = n_rows;
+    p1.cand = cand;
+    p1.cnt = cnt;
+    p1.tau = tau;
+    p1.fb_rows = fb_rows;
+    p1.fb_count = &sc->fb_count;
+    if ((e = run_pass(p1)) != cudaSuccess) return e;
 
     if (ev) cudaEventRecord(ev[3], stream);
     PrepScalars hsc;
@@ -1190,6 +1262,67 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         return e;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
     *h_fb_count = hsc.fb_count;
+
+    // ---- second pass: rows whose certificate failed, redone with four times longer lists.
+    //      Their cost on the exact kernel would be ~1000x a tensor-core row, so a data set on
+    //      which a few per cent of the rows fail must not fall off a cliff.  Skipped when most
+    //      rows fail (FP16 cannot resolve this data at all) or when there are only a handful.
+    const unsigned n_fb1 = hsc.fb_count;
+    if (n_fb1 >= 64 && n_fb1 <= (unsigned)n_rows / 2 && !getenv("PQH_TC_NO_PASS2") &&
+        debug_mode == 0) {
+        const int L1 = hsc.inexact ? lo.L : lo.L_exact;
+        int L2 = 4 * L1;
+        if (L2 > 192) L2 = 192;
+        if (L2 > L1) {
+            float *q2 = reinterpret_cast<float *>(w + lo.p2_q);
+            __half *xh2 = reinterpret_cast<__half *>(w + lo.p2_xh);
+            double *norm2 = reinterpret_cast<double *>(w + lo.p2_norm);
+            int *fb2 = reinterpret_cast<int *>(w + lo.p2_fb);
+            uint32_t *fb2_count = &sc->pad[1];
+            const float *src = self_join ? d_base : d_queries;
+            const int src_row0 = self_join ? 0 : q_row0;
+            for (unsigned done = 0; done < n_fb1; done += (unsigned)lo.p2_rows) {
+                const int n2 = (int)(n_fb1 - done < (unsigned)lo.p2_rows ? n_fb1 - done
+                                                                          : (unsigned)lo.p2_rows);
+                const int *ids = fb_rows + done;
+                TcLayout lo2;
+                tc_layout(n2, n2, nb, d, k, self_join, num_sms, &lo2, L2);
+                if (lo2.nlists > P2_MAX_LISTS || lo2.ns_tail > P2_MAX_LISTS)
+                    return cudaErrorInvalidValue;
+                gather_rows_kernel<<<(n2 + 7) / 8, 256, 0, stream>>>(src, src_row0, ids, n2, d, q2);
+                prep_rows_kernel<<<(n2 + 7) / 8, 256, 0, stream>>>(q2, n2, d, lo.d16, xh2, norm2,
+                                                                   nullptr, 0, sc);
+                *launches += 2;
+                if ((e = cudaMemsetAsync(&sc->tile_cursor, 0, sizeof(uint32_t), stream)) !=
+                    cudaSuccess)
+                    return e;
+                Pass p2;
+                p2.lo = &lo2;
+                p2.xh_q = xh2;
+                p2.a_rows = (uint64_t)n2;
+                p2.q_op_begin = 0;
+                p2.q_mat = q2;
+                p2.q_row_begin = 0;
+                p2.qnorm64 = norm2;
+                p2.row_ids = ids;
+                p2.n_rows = n2;
+                p2.cand = reinterpret_cast<key64_t *>(w + lo.p2_cand);
+                p2.cnt = reinterpret_cast<int *>(w + lo.p2_cnt);
+                p2.tau = reinterpret_cast<float *>(w + lo.p2_tau);
+                p2.fb_rows = fb2;
+                p2.fb_count = fb2_count;
+                if ((e = run_pass(p2)) != cudaSuccess) return e;
+            }
+            if ((e = cudaMemcpyAsync(&hsc, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost,
+                                     stream)) != cudaSuccess)
+                return e;
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            *h_fb_count = hsc.pad[1];
+            *d_fb_rows_out = fb2;
+            if (times) times->rows_pass2 = (long long)n_fb1;
+        }
+    }
+
     if (times) {
         times->candidates = 0;
         for (int i = 0; i < 32; ++i) times->candidates += (double)hsc.cand_total[i];
@@ -1199,17 +1332,19 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             cv.u = hsc.pad[0];
             times->eps_ratio_max = cv.f;
         }
-        if (getenv("PQH_TC_DEBUG")) {
+        if (dbg_env) {
             fprintf(stderr,
-                    "tc dbg: slow_chunks=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu | "
+                    "tc dbg: slow_tiles=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu | "
                     "epi warps: wait %.3g work %.3g cyc | mma thread: wait_b %.3g wait_acc %.3g "
-                    "total %.3g cyc (sums over CTAs)\n",
+                    "total %.3g cyc (sums over CTAs) | pass-1 failures %u\n",
                     hsc.dbg[0], hsc.dbg[1], hsc.dbg[2], hsc.dbg[3], (double)hsc.dbg[4],
                     (double)hsc.dbg[5], (double)hsc.dbg[6], (double)hsc.dbg[7],
-                    (double)hsc.cand_total[63]);
-            fprintf(stderr, "tc dbg: filter_tile cycles: load+maxima %.3g release(no hit) %.3g slow %.3g hard-shrink %.3g\n",
-                    (double)hsc.cand_total[40], (double)hsc.cand_total[41], (double)hsc.cand_total[42],
-                    (double)hsc.cand_total[43]);
+                    (double)hsc.cand_total[63], n_fb1);
+            fprintf(stderr,
+                    "tc dbg: filter_tile cycles: load+maxima %.3g release(no hit) %.3g slow %.3g "
+                    "hard-shrink %.3g\n",
+                    (double)hsc.cand_total[40], (double)hsc.cand_total[41],
+                    (double)hsc.cand_total[42], (double)hsc.cand_total[43]);
         }
         if (ev) {
             cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);

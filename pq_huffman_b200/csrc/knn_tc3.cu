@@ -258,7 +258,9 @@ knn_tc3_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             if (t_hi > args.n_btiles) t_hi = args.n_btiles;
             const int r = qt * 512 + (int)rank * 256 + row_l;
             const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const int self = (valid && args.self_join)
+                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
+                                 : -1;
             long long b_hi = (long long)t_hi * TC_BN;
             if (b_hi > args.nb) b_hi = args.nb;
             const int ib_hi = (int)b_hi;

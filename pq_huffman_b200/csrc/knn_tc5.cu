@@ -185,7 +185,9 @@ knn_tc5_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, const __h
             if (t_hi > args.n_btiles) t_hi = args.n_btiles;
             const int r = qt * TC_ROWS + row_in_cta;
             const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const int self = (valid && args.self_join)
+                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
+                                 : -1;
             const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
             key64_t *list = args.cand + slot * GCAP;
             float tau = valid ? NEG_INF : POS_INF;

@@ -49,6 +49,7 @@ struct TcArgs {
     int q_op_begin;  // row of row 0 inside the A operand tensor
     int nb;
     int self_join;
+    const int *row_ids;  // second pass: absolute query id of each row (null: q_begin + row)
     int n_qtiles, nsplit, tiles_per_split, n_btiles;
     // Tail of the work list: the last n_qtiles - q_tail0 query tiles (the partly filled last
     // round of the persistent grid) are cut into ns_tail base splits each so that every SM gets

@@ -215,7 +215,9 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
             const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
             const int r = qt * TC_ROWS + row_in_cta;
             const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join) ? args.q_begin + r : -1;
+            const int self = (valid && args.self_join)
+                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
+                                 : -1;
             const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
                                       : 0;
             key64_t *list = args.cand + slot * GCAP;

@@ -246,6 +246,7 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
             st->candidates += tt.candidates;
             if (tt.eps_ratio_max > st->eps_ratio_max) st->eps_ratio_max = tt.eps_ratio_max;
             st->inexact_operands = tt.inexact;
+            st->rows_second_pass += tt.rows_pass2;
         }
         rows_tc = n_rows - (long long)n_fb;
         if (n_fb > 0) {
@@ -391,6 +392,7 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, size_t 
             st.rows += sts[g].rows;
             st.rows_tensor += sts[g].rows_tensor;
             st.rows_exact += sts[g].rows_exact;
+            st.rows_second_pass += sts[g].rows_second_pass;
             st.launches += sts[g].launches;
             if (sts[g].ms_h2d > st.ms_h2d) st.ms_h2d = sts[g].ms_h2d;
             if (sts[g].ms_kernels > st.ms_kernels) st.ms_kernels = sts[g].ms_kernels;

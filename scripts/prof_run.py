@@ -27,9 +27,12 @@ d_d = torch.empty((n, k), dtype=torch.float32, device=dev)
 wb = knn.workspace_bytes(rows, n, d, k)
 d_w = torch.empty(wb, dtype=torch.uint8, device=dev)
 s = torch.cuda.Stream(device=dev)
+import time
 for rep in range(args.reps):
+    torch.cuda.synchronize(); _t0 = time.perf_counter()
     knn.search_device(0, n, n, d, k, d_x.data_ptr(), d_x.data_ptr(), True, 0, rows, d_a.data_ptr(),
                       d_d.data_ptr(), d_w.data_ptr(), wb, s.cuda_stream)
     torch.cuda.synchronize()
     st = knn.last_stats()
+    st['wall_ms'] = (time.perf_counter() - _t0) * 1e3
     print({key: (round(v, 3) if isinstance(v, float) else v) for key, v in st.items()}, flush=True)

@@ -186,6 +186,19 @@ def test_tensor_path_boundaries(oracle, n, d, k):
     assert_rows_equal(got, oracle.knn(x, None, k))
 
 
+@pytest.mark.parametrize("variant", ["2", "3", "4", "5"])
+def test_experimental_kernel_variants_stay_exact(monkeypatch, oracle, variant):
+    """The A/B variants kept in the tree (CTA-pair kernels, streaming kernel forced on a small d,
+    query operand in tensor memory) must keep producing the oracle's answer."""
+    monkeypatch.setenv("PQH_TC_VARIANT", variant)
+    x = synth.sift_like(6000, 128, seed=77)
+    got = knn.knn_full_thread(x, None, 17)
+    assert knn.last_stats()["rows_tensor"] > 0
+    assert_rows_equal(got, oracle.knn(x, None, 17))
+    g = synth.gist_like(4000, 96, seed=78)
+    assert_rows_equal(knn.knn_full_thread(g, None, 9), oracle.knn(g, None, 9))
+
+
 def test_mass_duplicates_through_tensor_path(oracle):
     """2500 copies of one vector: far more exact ties than the candidate lists hold, so the
     certificate cannot accept those rows (a non-candidate is exactly as close as the k-th

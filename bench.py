@@ -313,7 +313,7 @@ def run_ours(args):
             "metric": "exact kNN queries/sec", "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f16 tensor-core filter, f32 exact re-rank",
+            "vs_baseline": None, "dtype": "f32 (results: exact FP32 re-rank; candidate filter: f16 tensor cores, f32 accumulate)",
             "data": "synthetic",
             "config": {"workload": DESCRIPTIONS[args.workload], "n": n, "d": d, "k": num_nn,
                        "rows_per_gpu": per, "parallelism": f"query-rows/{world}",

@@ -11,17 +11,26 @@
 //   * the GEMM K dimension is [x'(d16) | fold(16)]: the A (query) side holds the
 //     constants (4096, 2, 2^-10, 0..), the B (base) side (-q1,-q2,-q3, 0..), so
 //     the accumulator IS S' and the epilogue is a bare threshold compare.
-// Nothing of the nq x nb score matrix reaches HBM: epilogue warps read the
-// accumulator from TMEM (tcgen05.ld), take the max of 32 columns per row and
-// only touch memory for the rare elements above the row's running threshold.
+// Nothing of the nq x nb score matrix reaches HBM: an epilogue thread owns one
+// query row, copies its 128 accumulator columns from TMEM to registers
+// (tcgen05.ld), reduces them to group maxima and only touches memory for the
+// rare elements above the row's running threshold (filter_tile_n in
+// knn_tc_common.cuh).
 //
 // Exactness.  Candidates (a superset of the top-L by S') are re-ranked by
 // knn_rerank_kernel with the scalar FP32 sequence of get_real_dist
 // (compute_nn_fast.c:304-311), giving distances bit-identical to the oracle.
 // A row is accepted only if a proven bound shows no non-candidate can beat its
-// k-th exact distance (see certificate in knn_rerank_kernel); other rows are
-// redone by the exact kernel (knn_exact.cu).  So the result is always the
-// oracle's, and the tensor cores only decide how fast it is found.
+// k-th exact distance (see certificate in knn_rerank_kernel); other rows get a
+// second pass with longer candidate lists and finally the exact kernel
+// (knn_exact.cu).  So the result is always the oracle's, and the tensor cores
+// only decide how fast it is found.
+//
+// Kernels in this file: knn_tc_kernel (default for d <= ~144: query tile
+// resident in shared memory), knn_tc2_kernel (CTA-pair experiment), the prep,
+// gather and re-rank kernels, and the host-side orchestration launch_knn_tc.
+// knn_tcs.cu holds the streaming kernel for larger d; knn_tc3.cu / knn_tc5.cu
+// two further measured experiments (profiles/README.md).
 #include <cuda.h>
 #include <cuda_fp16.h>
 

@@ -242,3 +242,31 @@ def test_in_library_multi_gpu_row_split(oracle):
     finally:
         knn.init([0])
     assert_rows_equal(got, oracle.knn(x, None, 17))
+
+
+def test_full_size_sift1m_properties():
+    """BASELINE configs[1] at full size (1M x 128, k = 16 + self).  The oracle cannot do 10^12
+    pairs in a test, so check size-independent properties on all rows and the oracle itself on
+    a sample of rows (its row-slice entry point does 1M distances per row)."""
+    from tests import oracle_ffi
+    n, d, k = 1_000_000, 128, 17
+    x = synth.sift_like(n, d)
+    a, dist = knn.knn_full_thread(x, None, k)
+    st = knn.last_stats()
+    assert st["rows"] == n and st["rows_tensor"] + st["rows_exact"] >= n
+    assert np.array_equal(a[:, 0], np.arange(n, dtype=np.int32))     # self first
+    assert np.all(dist[:, 0] == 0.0)
+    assert np.all(np.diff(dist, axis=1) >= 0)                        # ascending
+    assert a.min() >= 0 and a.max() < n
+    srt = np.sort(a, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])                         # k distinct ids per row
+    orc = oracle_ffi.Oracle()
+    rng = np.random.default_rng(1)
+    for r in rng.choice(n, 48, replace=False):
+        ea, ed = orc.knn_rows(x, None, k, int(r), int(r) + 1)
+        assert np.array_equal(a[r], ea[0]), r
+        assert np.array_equal(dist[r].view(np.uint32), ed[0].view(np.uint32)), r
+    # reported distances are the scalar definition for the reported pairs
+    for r in rng.choice(n, 200, replace=False):
+        j = int(a[r, 5])
+        assert np.float32(orc.dist(x[r], x[j])).view(np.uint32) == dist[r, 5].view(np.uint32)

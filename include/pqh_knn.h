@@ -123,6 +123,36 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
                           void *stream);
 
 /*
+ * Resident data set + block searches: the partitioned mode of compute_nn_fast
+ * (run(), compute_nn_fast.c:510-618) runs hundreds of self-joins over OVERLAPPING
+ * subsets ("blocks", fast_nn_block.h:4-11) of one file, re-reading the file and
+ * re-filling a block_t for each (fast_nn_block_loader2.c:86-146).  Here the file
+ * is uploaded once to every device of the context and a block is named by the
+ * row ids it holds; the rows are gathered on the device.
+ *
+ *   pqh_knn_dataset_load          rows: float32[n x d] on the host, row i at rows + i*ld
+ *                                 (ld = d + 1 for an .fvecs image); replaces any previous
+ *                                 data set and zeroes the stats, which then ACCUMULATE
+ *                                 over the block searches
+ *   pqh_knn_dataset_search_block  exactly knn_full_thread(2, m, m, d, k, blk, blk, NULL,
+ *                                 assign, dis, nt) for blk = the m rows row_ids[0..m) in
+ *                                 that order (run_block, compute_nn_fast.c:469-483):
+ *                                 assign holds positions WITHIN the block, column 0 is the
+ *                                 row itself.  `slot` selects the device (index into the
+ *                                 context's device list, 0 for one GPU); calls on different
+ *                                 slots may run concurrently from different host threads.
+ *   pqh_knn_dataset_release       frees the device copies
+ *   pqh_knn_host_alloc / _free    page-locked host memory for the result buffers of repeated
+ *                                 calls (plain malloc works too, at pageable-copy speed)
+ */
+int pqh_knn_dataset_load(int n, int d, const float *rows, long long ld);
+int pqh_knn_dataset_search_block(int slot, int m, const int *row_ids, int k, int *assign,
+                                 float *dis);
+void pqh_knn_dataset_release(void);
+void *pqh_knn_host_alloc(long long bytes);
+void pqh_knn_host_free(void *p);
+
+/*
  * Counters of the last search on this thread's context, for tests and
  * bench.py: how the rows were resolved and how many kernels were launched.
  */

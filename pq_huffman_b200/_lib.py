@@ -18,6 +18,11 @@ EXPORTS = (
     "pqh_knn_workspace_bytes",
     "pqh_knn_search_device",
     "pqh_knn_last_stats",
+    "pqh_knn_dataset_load",
+    "pqh_knn_dataset_search_block",
+    "pqh_knn_dataset_release",
+    "pqh_knn_host_alloc",
+    "pqh_knn_host_free",
 )
 
 
@@ -84,6 +89,16 @@ def load():
     lib.pqh_knn_search_device.restype = C.c_int
     lib.pqh_knn_last_stats.argtypes = [C.POINTER(Stats)]
     lib.pqh_knn_last_stats.restype = C.c_int
+    lib.pqh_knn_dataset_load.argtypes = [C.c_int, C.c_int, vp, C.c_longlong]
+    lib.pqh_knn_dataset_load.restype = C.c_int
+    lib.pqh_knn_dataset_search_block.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, vp]
+    lib.pqh_knn_dataset_search_block.restype = C.c_int
+    lib.pqh_knn_dataset_release.argtypes = []
+    lib.pqh_knn_dataset_release.restype = None
+    lib.pqh_knn_host_alloc.argtypes = [C.c_longlong]
+    lib.pqh_knn_host_alloc.restype = C.c_void_p
+    lib.pqh_knn_host_free.argtypes = [C.c_void_p]
+    lib.pqh_knn_host_free.restype = None
     del fp
     _lib = lib
     return lib

@@ -148,7 +148,7 @@ struct TcSmemTail {
     uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
 };
 
-template <int GCAP>
+template <int GCAP, bool PROF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -245,18 +245,18 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             int stage = 0, as = 0;
             uint32_t ph = 0, acc_ph = 0, a_ph = 0;
             long long mma_wait_b = 0, mma_wait_acc = 0;
-            const long long mma_t0 = clock64();
+            const long long mma_t0 = PROF ? clock64() : 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ItemInfo it = decode_item(args, item);
                 const int t_lo = it.t_lo, t_hi = it.t_hi;
                 ptx::mbar_wait(&tail.a_full, a_ph);
                 a_ph ^= 1;
                 for (int i = 0; i < t_hi - t_lo; ++i) {
-                    const long long m0 = clock64();
+                    const long long m0 = PROF ? clock64() : 0;
                     ptx::mbar_wait(&tail.b_full[stage], ph);
-                    const long long m1 = clock64();
+                    const long long m1 = PROF ? clock64() : 0;
                     ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
-                    const long long m2 = clock64();
+                    const long long m2 = PROF ? clock64() : 0;
                     mma_wait_b += m1 - m0;
                     mma_wait_acc += m2 - m1;
                     ptx::tc_fence_after_sync();
@@ -292,10 +292,12 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 }
                 ptx::umma_commit(&tail.a_empty);
             }
+            if (PROF) {
             PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
             atomicAdd(&scw->dbg[6], (unsigned long long)mma_wait_b);
             atomicAdd(&scw->dbg[7], (unsigned long long)mma_wait_acc);
             atomicAdd(&scw->cand_total[63], (unsigned long long)(clock64() - mma_t0));
+            }
         }
     } else {
         // ===================== epilogue: threshold filter =====================
@@ -331,10 +333,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
 
             int t0 = 0;
             for (int i = 0; i < t_hi - t_lo; ++i) {
-                const long long tw0 = clock64();
+                const long long tw0 = PROF ? clock64() : 0;
                 wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
                                                  cnt, list, ctr);
-                const long long tw1 = clock64();
+                const long long tw1 = PROF ? clock64() : 0;
                 t_wait += tw1 - tw0;
                 ptx::tc_fence_after_sync();
                 if (i == 0) {
@@ -359,7 +361,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 else
                     release();
                 ctr[3] += TC_BN / 32;
-                t_work += clock64() - tw1;
+                if (PROF) t_work += clock64() - tw1;
                 as ^= 1;
                 if (as == 0) acc_ph ^= 1;
             }
@@ -369,7 +371,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 args.cand_tau[slot] = tau;
             }
         }
-        if (lane == 0) {
+        if (PROF && lane == 0) {
             PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
             for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
             atomicAdd(&scw->dbg[4], (unsigned long long)t_wait);
@@ -1186,8 +1188,17 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             else LAUNCH_TC(knn_tc2_kernel<512>, tc2_smem_bytes<512>(args.plan), grid);
         } else {
             const int grid = n_items < num_sms ? n_items : num_sms;
-            if (pl.gcap == 256) LAUNCH_TC(knn_tc_kernel<256>, tc_smem_bytes<256>(args.plan), grid);
-            else LAUNCH_TC(knn_tc_kernel<512>, tc_smem_bytes<512>(args.plan), grid);
+            // the PROF instantiations carry the clock64()/counter instrumentation (PQH_TC_DEBUG)
+            if (debug_mode != 0) {
+                if (pl.gcap == 256)
+                    LAUNCH_TC((knn_tc_kernel<256, true>), tc_smem_bytes<256>(args.plan), grid);
+                else
+                    LAUNCH_TC((knn_tc_kernel<512, true>), tc_smem_bytes<512>(args.plan), grid);
+            } else if (pl.gcap == 256) {
+                LAUNCH_TC((knn_tc_kernel<256, false>), tc_smem_bytes<256>(args.plan), grid);
+            } else {
+                LAUNCH_TC((knn_tc_kernel<512, false>), tc_smem_bytes<512>(args.plan), grid);
+            }
         }
 #undef LAUNCH_TC
         ++*launches;

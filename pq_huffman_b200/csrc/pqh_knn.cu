@@ -82,6 +82,9 @@ struct DeviceCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf base, queries, assign, dis, work;
+    // resident data set of the block searches (pqh_knn_dataset_*)
+    DevBuf dataset, block_ids;
+    int ds_n = 0, ds_d = 0;
 };
 
 struct Context {
@@ -91,6 +94,10 @@ struct Context {
 };
 
 std::mutex g_mu;
+// one lock per device slot: block searches on different devices run concurrently, everything
+// that touches one device's buffers is serialised (lock order: g_mu, then g_dev_mu[slot])
+constexpr int MAX_DEVS = 16;
+std::mutex g_dev_mu[MAX_DEVS];
 Context *g_ctx = nullptr;
 int g_algo = PQH_ALGO_AUTO;
 
@@ -122,6 +129,8 @@ void destroy_ctx(Context *c) {
         d.assign.release();
         d.dis.release();
         d.work.release();
+        d.dataset.release();
+        d.block_ids.release();
         for (auto &e : d.ev)
             if (e) cudaEventDestroy(e);
         for (auto &e : d.kev)
@@ -146,6 +155,8 @@ int create_ctx(const int *devices, int n, Context **out) {
         return fail(PQH_ENODEV, "no CUDA device available (%s); libpqh_knn has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     }
+    if ((int)ids.size() > MAX_DEVS)
+        return fail(PQH_EINVAL, "at most %d devices per context", MAX_DEVS);
     Context *c = new Context();
     memset(&c->stats, 0, sizeof(c->stats));
     for (int id : ids) {
@@ -287,6 +298,7 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
                      int *assign, float *dis, pqh_knn_stats_t *st) {
     const int n_rows = q_end - q_begin;
     if (n_rows <= 0 || k <= 0) return PQH_OK;
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[&dc - c->devs.data()]);
     CU_TRY(cudaSetDevice(dc.dev));
     const size_t base_bytes = (size_t)nb * d * sizeof(float);
     const size_t out_elems = (size_t)n_rows * k;
@@ -329,6 +341,73 @@ int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int
                           static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
                           dc.work.p, dc.work.cap, dc.stream, st, false);
     if (rc) return rc;
+    CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
+    CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int), cudaMemcpyDeviceToHost,
+                           dc.stream));
+    CU_TRY(cudaMemcpyAsync(dis, dc.dis.p, out_elems * sizeof(float), cudaMemcpyDeviceToHost,
+                           dc.stream));
+    CU_TRY(cudaEventRecord(dc.ev[3], dc.stream));
+    CU_TRY(cudaStreamSynchronize(dc.stream));
+    if (st) {
+        st->ms_h2d += ev_ms(dc.ev[0], dc.ev[1]);
+        st->ms_kernels += ev_ms(dc.ev[1], dc.ev[2]);
+        st->ms_d2h += ev_ms(dc.ev[2], dc.ev[3]);
+        if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.kev[4], dc.kev[5]);
+    }
+    return PQH_OK;
+}
+
+// One warp per block row: out[r] = data[ids[r]] (what block_push's memcpy does on the host,
+// fast_nn_block.c:41-54).
+__global__ void gather_block_rows_kernel(const float *__restrict__ data, const int *__restrict__ ids,
+                                         int m, int d, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int n_warps = (int)((gridDim.x * (size_t)blockDim.x) >> 5);
+    for (int r = warp; r < m; r += n_warps) {
+        const float *src = data + (size_t)ids[r] * d;
+        float *dst = out + (size_t)r * d;
+        if ((d & 3) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            float4 *d4 = reinterpret_cast<float4 *>(dst);
+            for (int c = lane; c < d / 4; c += 32) d4[c] = __ldg(s4 + c);
+        } else {
+            for (int c = lane; c < d; c += 32) dst[c] = __ldg(src + c);
+        }
+    }
+}
+
+// Self-join among rows `row_ids` of the data set resident on `dc` (host pointers in and out).
+int dataset_search_block(Context *c, DeviceCtx &dc, int m, const int *row_ids, int k, int *assign,
+                         float *dis, pqh_knn_stats_t *st) {
+    if (m <= 0 || k <= 0) return PQH_OK;
+    const int d = dc.ds_d;
+    CU_TRY(cudaSetDevice(dc.dev));
+    const size_t out_elems = (size_t)m * k;
+    int rc;
+    if ((rc = dc.queries.ensure((size_t)m * d * sizeof(float)))) return rc;
+    if ((rc = dc.block_ids.ensure((size_t)m * sizeof(int)))) return rc;
+    if ((rc = dc.assign.ensure(out_elems * sizeof(int)))) return rc;
+    if ((rc = dc.dis.ensure(out_elems * sizeof(float)))) return rc;
+    if ((rc = dc.work.ensure(workspace_bytes(m, m, d, k, 1, dc.num_sms)))) return rc;
+
+    CU_TRY(cudaEventRecord(dc.ev[0], dc.stream));
+    CU_TRY(cudaMemcpyAsync(dc.block_ids.p, row_ids, (size_t)m * sizeof(int),
+                           cudaMemcpyHostToDevice, dc.stream));
+    float *blk = static_cast<float *>(dc.queries.p);
+    const int warps_per_cta = 8;
+    int grid = (m + warps_per_cta - 1) / warps_per_cta;
+    if (grid > 8 * dc.num_sms) grid = 8 * dc.num_sms;
+    gather_block_rows_kernel<<<grid, warps_per_cta * 32, 0, dc.stream>>>(
+        static_cast<const float *>(dc.dataset.p), static_cast<const int *>(dc.block_ids.p), m, d,
+        blk);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(dc.ev[1], dc.stream));
+    rc = search_on_device(dc, c->algo, m, d, k, blk, blk, 0, 1, 0, m,
+                          static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
+                          dc.work.p, dc.work.cap, dc.stream, st, false);
+    if (rc) return rc;
+    if (st) ++st->launches;
     CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
     CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int), cudaMemcpyDeviceToHost,
                            dc.stream));
@@ -492,6 +571,122 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
     if (!stream) CU_TRY(cudaStreamSynchronize(s));
     c->stats = st;
     return PQH_OK;
+}
+
+int pqh_knn_dataset_load(int n, int d, const float *rows, long long ld) {
+    if (n < 0 || d <= 0 || ld < d || (n > 0 && !rows))
+        return fail(PQH_EINVAL, "bad data set n=%d d=%d ld=%lld", n, d, ld);
+    std::lock_guard<std::mutex> lock(g_mu);
+    Context *c = nullptr;
+    int rc;
+    if ((rc = get_ctx(&c))) return rc;
+    memset(&c->stats, 0, sizeof(c->stats));
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceCtx &dc = c->devs[g];
+        std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);
+        CU_TRY(cudaSetDevice(dc.dev));
+        const size_t bytes = (size_t)n * d * sizeof(float);
+        if ((rc = dc.dataset.ensure(bytes ? bytes : 4))) return rc;
+        if (bytes)
+            CU_TRY(cudaMemcpy2DAsync(dc.dataset.p, (size_t)d * sizeof(float), rows,
+                                     (size_t)ld * sizeof(float), (size_t)d * sizeof(float),
+                                     (size_t)n, cudaMemcpyHostToDevice, dc.stream));
+        dc.ds_n = n;
+        dc.ds_d = d;
+    }
+    for (auto &dc : c->devs) {
+        CU_TRY(cudaSetDevice(dc.dev));
+        CU_TRY(cudaStreamSynchronize(dc.stream));
+    }
+    return PQH_OK;
+}
+
+int pqh_knn_dataset_search_block(int slot, int m, const int *row_ids, int k, int *assign,
+                                 float *dis) {
+    Context *c = nullptr;
+    int algo;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        c = g_ctx;
+        algo = g_algo;
+    }
+    if (!c) return fail(PQH_EINVAL, "no data set loaded");
+    if (slot < 0 || slot >= (int)c->devs.size())
+        return fail(PQH_EINVAL, "device slot %d out of range (context has %zu)", slot,
+                    c->devs.size());
+    DeviceCtx &dc = c->devs[slot];
+    if (m < 0 || k < 0 || (m > 0 && (!row_ids || (k > 0 && (!assign || !dis)))))
+        return fail(PQH_EINVAL, "bad block m=%d k=%d", m, k);
+    pqh_knn_stats_t st;
+    memset(&st, 0, sizeof(st));
+    auto t0 = std::chrono::steady_clock::now();
+    int rc;
+    {
+        std::lock_guard<std::mutex> dev_lock(g_dev_mu[slot]);
+        if (dc.ds_d <= 0) return fail(PQH_EINVAL, "no data set loaded");
+        for (int i = 0; i < m; ++i)
+            if (row_ids[i] < 0 || row_ids[i] >= dc.ds_n)
+                return fail(PQH_EINVAL, "row id %d at position %d outside the data set (%d rows)",
+                            row_ids[i], i, dc.ds_n);
+        c->algo = algo;
+        rc = dataset_search_block(c, dc, m, row_ids, k, assign, dis, &st);
+    }
+    const double ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> lock(g_mu);
+    pqh_knn_stats_t &a = c->stats;
+    a.rows += st.rows;
+    a.rows_tensor += st.rows_tensor;
+    a.rows_exact += st.rows_exact;
+    a.rows_second_pass += st.rows_second_pass;
+    a.launches += st.launches;
+    a.ms_total += ms;
+    a.ms_h2d += st.ms_h2d;
+    a.ms_kernels += st.ms_kernels;
+    a.ms_d2h += st.ms_d2h;
+    a.ms_prep += st.ms_prep;
+    a.ms_gemm += st.ms_gemm;
+    a.ms_rerank += st.ms_rerank;
+    a.ms_exact += st.ms_exact;
+    a.candidates += st.candidates;
+    if (st.eps_ratio_max > a.eps_ratio_max) a.eps_ratio_max = st.eps_ratio_max;
+    a.inexact_operands |= st.inexact_operands;
+    return rc;
+}
+
+void pqh_knn_dataset_release(void) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx) return;
+    for (size_t g = 0; g < g_ctx->devs.size(); ++g) {
+        std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);
+        DeviceCtx &dc = g_ctx->devs[g];
+        if (cudaSetDevice(dc.dev) != cudaSuccess) continue;
+        cudaStreamSynchronize(dc.stream);
+        dc.dataset.release();
+        dc.block_ids.release();
+        dc.ds_n = dc.ds_d = 0;
+    }
+}
+
+void *pqh_knn_host_alloc(long long bytes) {
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        Context *c = nullptr;
+        if (get_ctx(&c)) return nullptr;
+        cudaSetDevice(c->devs[0].dev);
+    }
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        fail(PQH_ENOMEM, "cudaHostAlloc(%lld bytes) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void pqh_knn_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int pqh_knn_last_stats(pqh_knn_stats_t *out) {

@@ -107,3 +107,36 @@ def search_device(device, nq_total, nb, d, k, d_base, d_queries, self_join, q_be
 
 def workspace_bytes(nq, nb, d, k):
     return int(_lib.load().pqh_knn_workspace_bytes(nq, nb, d, k))
+
+
+def dataset_load(rows, ld=None):
+    """Keep ``rows`` resident on every device of the context (pqh_knn_dataset_load).
+
+    ``rows`` is float32[n, d]; or, with ``ld``, a flat float32 buffer whose vector i starts at
+    element i*ld (an .fvecs image: pass the buffer from its second float on, ld = d + 1), in
+    which case ``rows`` must be a tuple (buffer, n, d).
+    """
+    lib = _lib.load()
+    if ld is None:
+        a = _as_f32(rows)
+        _check(lib.pqh_knn_dataset_load(a.shape[0], a.shape[1], a.ctypes.data, a.shape[1]))
+    else:
+        buf, n, d = rows
+        _check(lib.pqh_knn_dataset_load(n, d, buf.ctypes.data, ld))
+
+
+def dataset_search_block(row_ids, k, slot=0):
+    """Self-join among the rows ``row_ids`` of the resident data set: what the reference's
+    run_block gets from knn_full_thread for that block (ids are positions within the block)."""
+    lib = _lib.load()
+    ids = np.ascontiguousarray(row_ids, dtype=np.int32)
+    m = ids.shape[0]
+    assign = np.empty((m, k), dtype=np.int32)
+    dis = np.empty((m, k), dtype=np.float32)
+    _check(lib.pqh_knn_dataset_search_block(slot, m, ids.ctypes.data, k, assign.ctypes.data,
+                                            dis.ctypes.data))
+    return assign, dis
+
+
+def dataset_release():
+    _lib.load().pqh_knn_dataset_release()

@@ -1,7 +1,8 @@
-"""The native host driver pq_huffman_b200/pqh_compute_nn_fast (bulk I/O, single-block exact mode)
-must write the same bytes as the reference's own CLI: compared with oracle/_ref/
-compute_nn_fast_oracle (reference objects + CPU oracle) on inputs with ties and duplicates,
-including the kept temp file, and with the golden digests."""
+"""The native host driver pq_huffman_b200/pqh_compute_nn_fast (bulk I/O; exact single-block mode
+and the partitioned approximate mode over a data set resident in HBM) must write the same bytes
+as the reference's own CLI: compared with oracle/_ref/compute_nn_fast_oracle (reference objects +
+CPU oracle) on inputs with ties and duplicates, including the kept temp file, the blocks-info
+cache and the block statistics, and with the golden digests."""
 import hashlib
 import json
 import os
@@ -62,11 +63,78 @@ def test_host_cli_reproduces_golden_digest(tmp_path):
     assert not os.path.exists(tpl + "tmp.vecs")          # deleted by default, as the reference
 
 
-@pytest.mark.skipif(not os.path.exists(CLI), reason="host CLI not built")
-def test_host_cli_rejects_partitioned_mode(tmp_path):
-    x = synth.sift_like(100, 8)
+def _run_partitioned(binary, inp, outdir, k, extra=()):
+    os.makedirs(outdir, exist_ok=True)
+    tpl = str(outdir) + "/"
+    p = subprocess.run([binary, inp, tpl, str(k), "--temp-file", tpl + "tmp.vecs",
+                        "--num-threads", "4", *extra],
+                       capture_output=True, text=True, cwd=str(outdir))
+    assert p.returncode == 0, p.stderr[-800:]
+    return tpl, p.stdout
+
+
+PARTITIONED = [
+    # generator, n, d, k, flags: the reference's default geometry (5 splits x 3 boxes = 243 blocks)
+    ("ties", 5000, 16, 8, []),
+    # blocks large enough for the tensor-core path (9 blocks of ~10-25k rows)
+    ("sift_like", 60000, 32, 16, ["--num-dims", "2"]),
+    ("gist_like", 30000, 24, 5, ["--num-dims", "3", "--num-blocks-per-dim", "2",
+                                 "--block-overlap-fraction", "0.5"]),
+    # more neighbours asked than the small blocks hold: heaps keep {UINT_MAX, inf} slots
+    ("sift_like", 300, 8, 24, ["--num-dims", "4"]),
+]
+
+
+@pytest.mark.skipif(not (os.path.exists(CLI) and os.path.exists(REF_CLI)),
+                    reason="host CLI or oracle/_ref not built")
+@pytest.mark.parametrize("gen,n,d,k,flags", PARTITIONED)
+def test_host_cli_partitioned_mode_matches_reference_cli(tmp_path, gen, n, d, k, flags):
+    x = make_golden.make_input(gen, n, d, 70 + n)
     inp = str(tmp_path / "in.fvecs")
     vecs_io.write_xvecs(inp, x, "f")
-    p = subprocess.run([CLI, inp, str(tmp_path) + "/", "4", "--num-dims", "2"],
-                       capture_output=True, text=True)
-    assert p.returncode == 1 and "single-block" in p.stderr
+    extra = [*flags, "--no-delete-temp-file", "--with-blocks-stat"]
+    ours, out = _run_partitioned(CLI, inp, tmp_path / "ours", k,
+                                 [*extra, "--blocks-info-cache", str(tmp_path / "ours.cache")])
+    ref, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref", k,
+                              [*extra, "--blocks-info-cache", str(tmp_path / "ref.cache")])
+    for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs", "blocks_stat.txt"):
+        assert _sha(ours + name) == _sha(ref + name), f"{name} differs"
+    assert _sha(str(tmp_path / "ours.cache")) == _sha(str(tmp_path / "ref.cache"))
+    assert "blocks" in out
+    # second run: boundaries from the REFERENCE's cache file, same result
+    again, out2 = _run_partitioned(CLI, inp, tmp_path / "again", k,
+                                   [*flags, "--blocks-info-cache", str(tmp_path / "ref.cache")])
+    assert "Blocks info: Loaded" in out2
+    assert _sha(again + "nn_indices.ivecsl") == _sha(ref + "nn_indices.ivecsl")
+    assert _sha(again + "nn_dist.fvecsl") == _sha(ref + "nn_dist.fvecsl")
+    assert not os.path.exists(again + "tmp.vecs")
+
+
+@pytest.mark.skipif(not (os.path.exists(CLI) and os.path.exists(REF_CLI)),
+                    reason="host CLI or oracle/_ref not built")
+def test_host_cli_resumes_from_temp_file(tmp_path):
+    """--blocks-from and --no-init-temp-file (compute_nn_fast.c:545-555, 626-629): a run over
+    blocks [3,9) into fresh heaps, then a second run over blocks [6,9) that continues from the
+    REFERENCE's kept temp file -- both legs byte-identical to the reference doing the same."""
+    import shutil
+    n, d, k = 20000, 16, 10
+    x = make_golden.make_input("sift_like", n, d, 5)
+    inp = str(tmp_path / "in.fvecs")
+    vecs_io.write_xvecs(inp, x, "f")
+    flags = ["--num-dims", "2", "--no-delete-temp-file"]
+    ours, _ = _run_partitioned(CLI, inp, tmp_path / "ours", k, [*flags, "--blocks-from", "3"])
+    ref, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref", k, [*flags, "--blocks-from", "3"])
+    for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
+        assert _sha(ours + name) == _sha(ref + name), f"leg 1: {name} differs"
+    whole, _ = _run_partitioned(REF_CLI, inp, tmp_path / "whole", k, flags)
+    assert _sha(whole + "nn_indices.ivecsl") != _sha(ref + "nn_indices.ivecsl")  # a partial result
+
+    for who in ("ours2", "ref2"):
+        os.makedirs(tmp_path / who)
+        shutil.copy(ref + "tmp.vecs", str(tmp_path / who / "tmp.vecs"))
+    ours2, _ = _run_partitioned(CLI, inp, tmp_path / "ours2", k,
+                                [*flags, "--blocks-from", "6", "--no-init-temp-file"])
+    ref2, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref2", k,
+                               [*flags, "--blocks-from", "6", "--no-init-temp-file"])
+    for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
+        assert _sha(ours2 + name) == _sha(ref2 + name), f"leg 2: {name} differs"

@@ -270,3 +270,48 @@ def test_full_size_sift1m_properties():
     for r in rng.choice(n, 200, replace=False):
         j = int(a[r, 5])
         assert np.float32(orc.dist(x[r], x[j])).view(np.uint32) == dist[r, 5].view(np.uint32)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_resident_dataset_block_searches(oracle, algo):
+    """pqh_knn_dataset_search_block == knn_full_thread on the gathered block (run_block,
+    compute_nn_fast.c:469-483): large blocks (tensor-core path), small ones (exact kernel),
+    unsorted row ids, single-row and empty blocks, repeated calls on one resident data set."""
+    n, d = 30000, 32
+    x = synth.with_duplicates_and_ties(synth.sift_like(n, d, seed=12), n_dups=30, n_ties=30)
+    knn.set_algo(algo)
+    knn.dataset_load(x)
+    rng = np.random.default_rng(3)
+    try:
+        for m, k, ordered in [(9000, 17, True), (500, 9, True), (4000, 17, False), (2, 2, True),
+                              (1, 1, True), (n, 5, True)]:
+            ids = rng.choice(n, size=m, replace=False).astype(np.int32)
+            if ordered:
+                ids.sort()
+            got = knn.dataset_search_block(ids, k)
+            assert_rows_equal(got, oracle.knn(x[ids], None, k))
+        a, dd = knn.dataset_search_block(np.empty(0, dtype=np.int32), 3)
+        assert a.shape == (0, 3)
+        st = knn.last_stats()
+        assert st["rows"] == 9000 + 500 + 4000 + 2 + 1 + n          # stats accumulate
+        with pytest.raises(knn.PqhError):
+            knn.dataset_search_block(np.array([0, n], dtype=np.int32), 2)
+    finally:
+        knn.dataset_release()
+    with pytest.raises(knn.PqhError):
+        knn.dataset_search_block(np.array([0, 1], dtype=np.int32), 2)
+
+
+def test_resident_dataset_from_fvecs_image(oracle):
+    n, d = 6000, 24
+    x = synth.gist_like(n, d, seed=8)
+    img = np.empty((n, d + 1), dtype=np.float32)
+    img[:, 0] = np.array([d], dtype=np.int32).view(np.float32)[0]
+    img[:, 1:] = x
+    flat = img.reshape(-1)
+    knn.dataset_load((flat[1:], n, d), ld=d + 1)
+    try:
+        ids = np.arange(100, 5100, dtype=np.int32)
+        assert_rows_equal(knn.dataset_search_block(ids, 6), oracle.knn(x[ids], None, 6))
+    finally:
+        knn.dataset_release()

@@ -322,6 +322,13 @@ typedef struct {
     ring_slot_t *ring;
     int ring_len, num_devices;
     long long begin, end;
+    /* what the row-finding stage needs */
+    const pqh_partition_t *part;
+    const float *cols;
+    long long n, blocks_on_pass;
+    int prefix_len, k, threads;
+    FILE *blocks_stat;
+    double t_rows;
 } pipeline_t;
 
 typedef struct {
@@ -363,6 +370,33 @@ static void *device_thread(void *arg) {
         pthread_cond_broadcast(&pl->cv);
         pthread_mutex_unlock(&pl->mu);
     }
+    return NULL;
+}
+
+/* First stage: the rows of each block, in block order, as ring slots come free (a slot is
+ * released by the merge of the block ring_len places earlier). */
+static void *rows_thread(void *arg) {
+    pipeline_t *pl = (pipeline_t *)arg;
+    long long *counts = (long long *)malloc(sizeof(long long) * (size_t)pl->threads);
+    for (long long b = pl->begin; b < pl->end; ++b) {
+        ring_slot_t *s = pl->ring + (b - pl->begin) % pl->ring_len;
+        pthread_mutex_lock(&pl->mu);
+        while (s->state != SLOT_FREE) pthread_cond_wait(&pl->cv, &pl->mu);
+        pthread_mutex_unlock(&pl->mu);
+        const double tr = now_s();
+        const long long pass_first =
+            pl->begin + (b - pl->begin) / pl->blocks_on_pass * pl->blocks_on_pass;
+        s->m = block_rows(pl->threads, pl->part, pl->cols, pl->n, b, pass_first, pl->prefix_len,
+                          s->ids, counts);
+        s->k1 = (int)(s->m - 1 < pl->k ? s->m - 1 : pl->k) + 1;
+        if (pl->blocks_stat) fprintf(pl->blocks_stat, "%d ", (int)s->m);
+        pl->t_rows += now_s() - tr;
+        pthread_mutex_lock(&pl->mu);
+        s->state = SLOT_READY;
+        pthread_cond_broadcast(&pl->cv);
+        pthread_mutex_unlock(&pl->mu);
+    }
+    free(counts);
     return NULL;
 }
 
@@ -559,38 +593,36 @@ int main(int argc, char **argv) {
         pthread_cond_init(&pl.cv, NULL);
         pl.num_devices = pqh_knn_device_count();
         if (pl.num_devices < 1) pl.num_devices = 1;
-        pl.ring_len = 2 * pl.num_devices;
+        pl.ring_len = 2 * pl.num_devices + 2;
         pl.begin = begin;
         pl.end = end;
+        pl.part = &part;
+        pl.cols = cols;
+        pl.n = n;
+        pl.blocks_on_pass = blocks_on_pass;
+        pl.prefix_len = prefix_len;
+        pl.k = k;
+        pl.threads = nt > 2 ? nt / 2 : 1; /* the other half of the cores merges meanwhile */
+        pl.blocks_stat = bs;
+        pl.t_rows = 0;
         pl.ring = (ring_slot_t *)calloc((size_t)pl.ring_len, sizeof(ring_slot_t));
         for (int i = 0; i < pl.ring_len; ++i) pl.ring[i].ids = (int *)malloc(sizeof(int) * (size_t)n);
-        long long *counts = (long long *)malloc(sizeof(long long) * (size_t)nt);
+        pthread_t rows_th;
         pthread_t *dth = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)pl.num_devices);
         device_thread_t *dts = (device_thread_t *)malloc(sizeof(device_thread_t) * (size_t)pl.num_devices);
+        pthread_create(&rows_th, NULL, rows_thread, &pl);
         for (int g = 0; g < pl.num_devices; ++g) {
             dts[g].pl = &pl;
             dts[g].device_slot = g;
             pthread_create(dth + g, NULL, device_thread, dts + g);
         }
-        long long next = begin; /* first block not yet handed to a device */
+        /* three stages run concurrently: rows of block b+.. (rows_thread), search of the blocks
+         * in between (one thread per device), merge of block b (here, in block order) */
+        const int merge_threads = nt > 2 ? nt - pl.threads : 1;
         for (long long b = begin; b < end; ++b) {
             if ((b - begin) % 10 == 0)
                 printf("Start block %6lld / %6lld (%6lld / %6lld)\n", b - begin, end - begin, b,
                        part.num_blocks);
-            /* keep every device busy while this thread merges: hand out up to block b + G */
-            for (; next < end && next <= b + pl.num_devices; ++next) {
-                ring_slot_t *s = pl.ring + (next - begin) % pl.ring_len;
-                const double tr = now_s();
-                const long long pass_first = begin + (next - begin) / blocks_on_pass * blocks_on_pass;
-                s->m = block_rows(nt, &part, cols, n, next, pass_first, prefix_len, s->ids, counts);
-                s->k1 = (int)(s->m - 1 < k ? s->m - 1 : k) + 1;
-                if (bs) fprintf(bs, "%d ", (int)s->m);
-                t_rows += now_s() - tr;
-                pthread_mutex_lock(&pl.mu);
-                s->state = SLOT_READY;
-                pthread_cond_broadcast(&pl.cv);
-                pthread_mutex_unlock(&pl.mu);
-            }
             ring_slot_t *s = pl.ring + (b - begin) % pl.ring_len;
             const double tw = now_s();
             pthread_mutex_lock(&pl.mu);
@@ -598,11 +630,17 @@ int main(int argc, char **argv) {
             pthread_mutex_unlock(&pl.mu);
             const double tm = now_s();
             t_wait_gpu += tm - tw;
-            if (s->m > 1) merge_block(nt, heaps, k, s->k1, s->m, s->ids, s->assign, s->dis);
+            if (s->m > 1)
+                merge_block(merge_threads, heaps, k, s->k1, s->m, s->ids, s->assign, s->dis);
             t_merge_only += now_s() - tm;
             rows_in_blocks += s->m;
+            pthread_mutex_lock(&pl.mu);
             s->state = SLOT_FREE;
+            pthread_cond_broadcast(&pl.cv);
+            pthread_mutex_unlock(&pl.mu);
         }
+        pthread_join(rows_th, NULL);
+        t_rows = pl.t_rows;
         for (int g = 0; g < pl.num_devices; ++g) pthread_join(dth[g], NULL);
         for (int i = 0; i < pl.ring_len; ++i) {
             free(pl.ring[i].ids);
@@ -610,7 +648,6 @@ int main(int argc, char **argv) {
             pqh_knn_host_free(pl.ring[i].dis);
         }
         free(pl.ring);
-        free(counts);
         free(dth);
         free(dts);
     }
@@ -646,5 +683,6 @@ int main(int argc, char **argv) {
            t_init - t_part, t_knn - t_init, t_rows, t_wait_gpu, t_merge_only, s.ms_h2d, s.ms_kernels,
            s.ms_d2h, s.rows_tensor, s.rows_exact, t_end - t_knn, t_end - t0);
     pqh_knn_shutdown();
+    printf("context released in %.3f s\n", now_s() - t_end);
     return 0;
 }

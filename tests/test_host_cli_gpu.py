@@ -138,3 +138,29 @@ def test_host_cli_resumes_from_temp_file(tmp_path):
                                [*flags, "--blocks-from", "6", "--no-init-temp-file"])
     for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
         assert _sha(ours2 + name) == _sha(ref2 + name), f"leg 2: {name} differs"
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif(not (os.path.exists(CLI) and os.path.exists(REF_CLI)) or _n_devices() < 2,
+                    reason="needs the host CLI, oracle/_ref and two GPUs")
+def test_host_cli_partitioned_mode_on_two_gpus(tmp_path):
+    """PQH_DEVICES=0,1: blocks alternate between the devices, merges stay in block order, so the
+    bytes do not change."""
+    x = make_golden.make_input("sift_like", 50000, 32, 11)
+    inp = str(tmp_path / "in.fvecs")
+    vecs_io.write_xvecs(inp, x, "f")
+    flags = ["--num-dims", "3", "--no-delete-temp-file"]
+    os.makedirs(tmp_path / "two")
+    tpl = str(tmp_path / "two") + "/"
+    env = dict(os.environ, PQH_DEVICES="0,1")
+    env.pop("CUDA_VISIBLE_DEVICES", None)
+    p = subprocess.run([CLI, inp, tpl, "12", "--temp-file", tpl + "tmp.vecs", *flags],
+                       capture_output=True, text=True, cwd=tpl, env=env)
+    assert p.returncode == 0, p.stderr[-800:]
+    ref, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref", 12, flags)
+    for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
+        assert _sha(tpl + name) == _sha(ref + name), f"{name} differs"

@@ -315,3 +315,33 @@ def test_resident_dataset_from_fvecs_image(oracle):
         assert_rows_equal(knn.dataset_search_block(ids, 6), oracle.knn(x[ids], None, 6))
     finally:
         knn.dataset_release()
+
+
+@pytest.mark.skipif(_n_devices() < 2, reason="needs two GPUs")
+def test_resident_dataset_blocks_on_two_gpus_concurrently(oracle):
+    """Whole blocks round-robin over the devices (small-block alternative): two host
+    threads search different blocks of the same resident data set on slots 0 and 1 at once."""
+    import threading
+    n, d, k = 40000, 64, 11
+    x = synth.sift_like(n, d, seed=21)
+    rng = np.random.default_rng(9)
+    blocks = [np.sort(rng.choice(n, size=m, replace=False)).astype(np.int32)
+              for m in (12000, 9000, 700, 15000, 3000, 11000)]
+    out = [None] * len(blocks)
+    try:
+        knn.init([0, 1])
+        knn.dataset_load(x)
+
+        def work(slot):
+            for i in range(slot, len(blocks), 2):
+                out[i] = knn.dataset_search_block(blocks[i], k, slot=slot)
+
+        th = [threading.Thread(target=work, args=(s,)) for s in (0, 1)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert knn.last_stats()["rows"] == sum(len(b) for b in blocks)
+    finally:
+        knn.dataset_release()
+        knn.init([0])
+    for ids, got in zip(blocks, out):
+        assert_rows_equal(got, oracle.knn(x[ids], None, k))

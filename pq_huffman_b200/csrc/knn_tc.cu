@@ -873,7 +873,11 @@ int pick_L(int kcap, bool inexact) {
     return L;
 }
 // list capacity: the filter checks it once per tile, after up to TC_BN (128) appends
-int pick_gcap(int L) { return L <= 96 ? 256 : 512; }
+int pick_gcap(int L) {
+    static const char *e = getenv("PQH_TC_GCAP");  // experiments: 256 or 512
+    if (e && (atoi(e) == 256 || atoi(e) == 512) && L <= 96) return atoi(e);
+    return L <= 96 ? 256 : 512;
+}
 
 template <int GCAP>
 size_t tc2_smem_bytes(const TcPlan &p) {

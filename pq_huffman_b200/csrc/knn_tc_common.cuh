@@ -228,8 +228,11 @@ __device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lan
 // Predicated append of (ordered(-score), id) to a row's candidate list: no branch.
 __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint32_t score_bits,
                                           int id) {
-    const uint32_t u = score_bits ^ 0x80000000u;                          // bits of -score
-    const uint32_t hi = u ^ ((uint32_t)((int)u >> 31) | 0x80000000u);     // float_to_ordered
+    // float_to_ordered(-score) straight from the bits of score: two instructions
+    // hi = bits ^ (~sign & 0x7fffffff)
+    uint32_t sign, hi;
+    asm("shr.s32 %0, %1, 31;" : "=r"(sign) : "r"(score_bits));
+    asm("lop3.b32 %0, %1, %2, 0x7fffffff, 0xD2;" : "=r"(hi) : "r"(score_bits), "r"(sign));
     const key64_t key = ((key64_t)hi << 32) | (key64_t)(uint32_t)id;
     asm volatile(
         "{\n\t"
@@ -307,13 +310,22 @@ __device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool
     }
     ++ctr[0];
     const int id_lim = special ? ib_hi : 0x7fffffff;
+    // the id checks (ragged last tile, the row's own column) are only compiled into the copy of
+    // the scan that "special" tiles take; the choice is made warp-uniform
+    const bool any_special = __any_sync(0xffffffffu, special);
     auto scan8 = [&](const uint32_t(&v8)[8], int q) {
         const int col0 = col_base + q * 8;
+        if (any_special) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int id = col0 + j;
-            const bool p = (__uint_as_float(v8[j]) > tau) & (id < id_lim) & (id != self);
-            append_if(p, list, cnt, v8[j], id);
+            for (int j = 0; j < 8; ++j) {
+                const int id = col0 + j;
+                const bool p = (__uint_as_float(v8[j]) > tau) & (id < id_lim) & (id != self);
+                append_if(p, list, cnt, v8[j], id);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                append_if(__uint_as_float(v8[j]) > tau, list, cnt, v8[j], col0 + j);
         }
     };
     const int q1 = __ffs(groups) - 1;

@@ -90,3 +90,41 @@ def test_blocks_to_keeps_the_reference_arithmetic(tmp_path):
     ref, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref", 4, flags)
     for name in ("nn_indices.ivecsl", "nn_dist.fvecsl"):
         assert _sha(ours + name) == _sha(ref + name), f"{name} differs"
+
+
+def test_blocks_per_pass_only_groups_blocks(tmp_path):
+    """--num-dimensions-at-pass P makes the reference load B^P blocks per pass over the file,
+    sharing a prefix test (fast_nn_block_loader2.c:111-118); the result cannot depend on it."""
+    x = make_golden.make_input("gist_like", 2500, 10, 17)
+    inp = str(tmp_path / "in.fvecs")
+    vecs_io.write_xvecs(inp, x, "f")
+    flags = ["--num-dims", "3"]
+    plain, _ = _run_partitioned(SHIM, inp, tmp_path / "plain", 6, flags)
+    for p in ("1", "2", "3"):
+        grouped, _ = _run_partitioned(SHIM, inp, tmp_path / ("pass" + p), 6,
+                                      [*flags, "--num-dimensions-at-pass", p])
+        for name in ("nn_indices.ivecsl", "nn_dist.fvecsl"):
+            assert _sha(grouped + name) == _sha(plain + name), f"P={p}: {name} differs"
+
+
+def test_driver_rejects_bad_input(tmp_path):
+    import subprocess
+    x = make_golden.make_input("sift_like", 50, 8, 1)
+    inp = str(tmp_path / "in.fvecs")
+    vecs_io.write_xvecs(inp, x, "f")
+    tpl = str(tmp_path) + "/"
+
+    def run(*args):
+        return subprocess.run([SHIM, *args], capture_output=True, text=True, cwd=str(tmp_path))
+
+    assert run(inp, tpl).returncode == 1                                   # too few arguments
+    assert run(inp, tpl, "4", "--no-such-flag").returncode == 1
+    assert run(str(tmp_path / "missing.fvecs"), tpl, "4").returncode == 1
+    assert run(inp, tpl, "0").returncode == 1                               # num_nn < 1
+    assert run(inp, tpl, "4", "--num-dims", "9").returncode == 1            # more splits than dims
+    p = run(inp, tpl, "4", "--num-dims", "1", "--no-init-temp-file", "--temp-file",
+            str(tmp_path / "absent.vecs"))
+    assert p.returncode == 1 and "cannot read" in p.stderr
+    with open(str(tmp_path / "ragged.fvecs"), "wb") as f:                   # not whole rows
+        f.write(open(inp, "rb").read()[:-3])
+    assert run(str(tmp_path / "ragged.fvecs"), tpl, "4").returncode == 1

@@ -11,7 +11,7 @@ import pytest
 from pq_huffman_b200 import vecs_io
 from tests import oracle_ffi
 from tests.golden import make_golden
-from tests.test_host_cli_gpu import REF_CLI, _run, _run_partitioned, _sha
+from tests.test_host_cli_gpu import REF_CLI, _golden_case, _run, _run_partitioned, _sha
 
 SHIM = os.path.join(oracle_ffi.LIB_DIR, "pqh_compute_nn_fast_shim")
 
@@ -128,3 +128,8 @@ def test_driver_rejects_bad_input(tmp_path):
     with open(str(tmp_path / "ragged.fvecs"), "wb") as f:                   # not whole rows
         f.write(open(inp, "rb").read()[:-3])
     assert run(str(tmp_path / "ragged.fvecs"), tpl, "4").returncode == 1
+
+
+@pytest.mark.parametrize("name", ["cli_single_block", "cli_partitioned"])
+def test_golden_digests(tmp_path, name):
+    _golden_case(SHIM, tmp_path, name)

@@ -50,17 +50,29 @@ def test_host_cli_matches_reference_cli(tmp_path, gen, n, d, k):
         assert _sha(ours + name) == _sha(ref + name), f"{name} differs"
 
 
-@pytest.mark.skipif(not os.path.exists(CLI), reason="host CLI not built")
-def test_host_cli_reproduces_golden_digest(tmp_path):
-    c = json.load(open(os.path.join(ROOT, "tests", "golden", "index.json")))["cli"][
-        "cli_single_block"]
+def _golden_case(binary, tmp_path, name):
+    """Run `binary` on the committed golden input of tests/golden/index.json["cli"][name] and
+    compare the digests of both output files (made by the reference CLI + oracle,
+    tests/golden/make_golden.py)."""
+    c = json.load(open(os.path.join(ROOT, "tests", "golden", "index.json")))["cli"][name]
     x = make_golden.make_input("ties", c["n"], c["d"], c["seed"])
     inp = str(tmp_path / "in.fvecs")
     vecs_io.write_xvecs(inp, x, "f")
-    tpl = _run(CLI, inp, tmp_path / "o", c["num_nn"])
+    assert hashlib.sha256(x.tobytes()).hexdigest() == c["input_sha256"]
+    os.makedirs(tmp_path / "o", exist_ok=True)
+    tpl = str(tmp_path / "o") + "/"
+    p = subprocess.run([binary, inp, tpl, str(c["num_nn"]), *c["args"], "--temp-file",
+                        tpl + "tmp.vecs"], capture_output=True, text=True, cwd=tpl)
+    assert p.returncode == 0, p.stderr[-800:]
     assert _sha(tpl + "nn_indices.ivecsl") == c["nn_indices.ivecsl"]
     assert _sha(tpl + "nn_dist.fvecsl") == c["nn_dist.fvecsl"]
     assert not os.path.exists(tpl + "tmp.vecs")          # deleted by default, as the reference
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="host CLI not built")
+@pytest.mark.parametrize("name", ["cli_single_block", "cli_partitioned"])
+def test_host_cli_reproduces_golden_digest(tmp_path, name):
+    _golden_case(CLI, tmp_path, name)
 
 
 def _run_partitioned(binary, inp, outdir, k, extra=()):

@@ -305,15 +305,24 @@ def run_ours(args):
         achieved = (flops_per_launch / (gemm_ms_max / launches_gemm / 1e3) / 1e12
                     if gemm_ms_max > 0 else 0.0)
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        # which tensor-core flavour ran: uint8-valued data takes the exact INT8 path
+        int8_path = st_acc["inexact_operands"] == 2
+        operands = ("u8 x s8 -> s32 (tcgen05.mma kind::i8, exact scores)" if int8_path else
+                    "f16 x f16 -> f32 (tcgen05.mma kind::f16)")
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload)
+            tj = json.load(open(tpath))
+            traffic = tj.get(args.workload + ("_i8" if int8_path else ""))
         line = {
             "metric": "exact kNN queries/sec", "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (results: exact FP32 re-rank; candidate filter: f16 tensor cores, f32 accumulate)",
+            "vs_baseline": None,
+            "dtype": ("f32 (results: exact FP32 re-rank; candidate filter: int8 tensor cores, "
+                      "s32 accumulate)" if int8_path else
+                      "f32 (results: exact FP32 re-rank; candidate filter: f16 tensor cores, "
+                      "f32 accumulate)"),
             "data": "synthetic",
             "config": {"workload": DESCRIPTIONS[args.workload], "n": n, "d": d, "k": num_nn,
                        "rows_per_gpu": per, "parallelism": f"query-rows/{world}",
@@ -328,7 +337,13 @@ def run_ours(args):
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": f"{peak_src} bf16_tflops_sustained (kernel runs inside a "
                                         "long step)",
-                         "ms_per_launch": gemm_ms_max / launches_gemm, "traffic": traffic},
+                         "ms_per_launch": gemm_ms_max / launches_gemm, "traffic": traffic,
+                         "operands": operands,
+                         # the contract's denominator stays the measured bf16 peak; the INT8
+                         # pipe's own nominal dense peak on B200 is twice the 16-bit one
+                         "peak_operand_format_nominal": 4500.0 if int8_path else 2250.0,
+                         "frac_operand_format_nominal":
+                             achieved / (4500.0 if int8_path else 2250.0)},
             "phases_ms": {key: st_acc[key] for key in ("ms_prep", "ms_gemm", "ms_rerank",
                                                        "ms_exact")},
             "rows_exact_fallback": st_acc["rows_exact"],

@@ -171,7 +171,9 @@ typedef struct pqh_knn_stats {
     double ms_exact;           /* exact FP32 kernel (fallback rows or PQH_ALGO_EXACT) */
     double candidates;         /* candidates re-ranked, summed over rows */
     double eps_ratio_max;      /* $PQH_TC_CHECK_EPS set: max |tensor score - fp64 score| / bound */
-    long long inexact_operands;/* 1 if some FP16 operand was rounded (not integer-like data) */
+    long long inexact_operands;/* 1 if some FP16 operand was rounded (not integer-like data);
+                                  2 if the data are integers in [0,255] and the exact INT8
+                                  tensor-core path was taken ($PQH_TC_I8=0 disables it) */
 } pqh_knn_stats_t;
 int pqh_knn_last_stats(pqh_knn_stats_t *out);
 

@@ -41,6 +41,9 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include "knn_tc_common.cuh"
+#include "knn_tc_i8.cuh"
+
+#include <type_traits>
 
 namespace pqh {
 
@@ -136,6 +139,59 @@ __global__ void fold_const_kernel(__half *__restrict__ fa) {
     fa[i] = __float2half_rn(v);
 }
 
+// Integer path (knn_tc_i8.cuh), one warp per row: the row as 8-bit integers -- u8 x for the A
+// (query) operand, s8 x - 128 for the B (base) operand -- zero-padded to d32 bytes; FP64 squared
+// norm; for base rows the 32 s8 fold digits of G = ceil(|y|^2 / 2).  sc->pad[2] collects the
+// reasons the integer path cannot be used: bit 0 = a value is not an integer in [0, 255],
+// bit 1 = |y|^2 beyond the capacity of the fold columns.
+__global__ void __launch_bounds__(256)
+prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t *__restrict__ out,
+                    double *__restrict__ norm64, int8_t *__restrict__ fold, int as_base,
+                    PrepScalars *__restrict__ sc) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float *xr = x + (size_t)row * d;
+    uint8_t *o = out + (size_t)row * d32;
+    double acc = 0.0;
+    bool bad = false;
+    for (int i = lane; i < d32; i += 32) {
+        const float v = i < d ? xr[i] : 0.0f;
+        const int iv = (int)v;
+        if (!(v >= 0.0f && v <= 255.0f) || (float)iv != v) bad = true;
+        uint8_t b = 0;
+        if (i < d) b = as_base ? (uint8_t)(int8_t)(iv - 128) : (uint8_t)iv;
+        o[i] = b;
+        acc += (double)v * (double)v;
+    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+    unsigned flags = __any_sync(0xffffffffu, bad) ? 1u : 0u;
+    if (norm64 && lane == 0) norm64[row] = acc;
+    if (fold) {
+        const long long G = ((long long)acc + 1) / 2;
+        const long long q = G / I8_FOLD_UNIT;
+        const int r = (int)(G % I8_FOLD_UNIT);
+        if (q >= I8_FOLD_FULL) flags |= 2u;
+        int b = 0;
+        if (lane < I8_FOLD_FULL) {
+            if (lane < q) b = -128;
+            else if (lane == q) b = -(r / 255);
+        } else {
+            const int r2 = r % 255, first = r2 < 127 ? r2 : 127;
+            b = lane == I8_FOLD_FULL ? -first : -(r2 - first);
+        }
+        fold[(size_t)row * 32 + lane] = (int8_t)b;
+    }
+    if (flags && lane == 0) atomicOr(&sc->pad[2], flags);
+}
+
+__global__ void fold_const_i8_kernel(uint8_t *__restrict__ fa) {
+    // [256 x 32]: what every query row multiplies the fold digits by
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TC_ROWS * 32) return;
+    fa[i] = (i % 32) < I8_FOLD_FULL ? 255 : 1;
+}
+
 // ------------------------------------------------------------------------------------
 // main kernel
 template <int GCAP>
@@ -148,7 +204,8 @@ struct TcSmemTail {
     uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
 };
 
-template <int GCAP, bool PROF>
+// I8: integer operands and scores (knn_tc_i8.cuh); everything else is shared.
+template <int GCAP, bool PROF, bool I8>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -241,7 +298,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(128, TC_BN);
+            constexpr uint32_t idesc =
+                I8 ? ptx::make_idesc_i8_u8s8(128, TC_BN) : ptx::make_idesc_f16(128, TC_BN);
             int stage = 0, as = 0;
             uint32_t ph = 0, acc_ph = 0, a_ph = 0;
             long long mma_wait_b = 0, mma_wait_acc = 0;
@@ -274,9 +332,14 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
 #pragma unroll
                             for (int g = 0; g < 2; ++g) {
                                 const uint32_t a_addr = a_base + sg.a_off + g * 128 * sg.bytes;
-                                ptx::umma_f16(tmem_base + (uint32_t)(as * 256 + g * 128),
-                                              ptx::make_smem_desc(a_addr + kk * 32, sbo, lay), bd,
-                                              idesc, acc);
+                                if constexpr (I8)
+                                    ptx::umma_i8(tmem_base + (uint32_t)(as * 256 + g * 128),
+                                                 ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
+                                                 bd, idesc, acc);
+                                else
+                                    ptx::umma_f16(tmem_base + (uint32_t)(as * 256 + g * 128),
+                                                  ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
+                                                  bd, idesc, acc);
                             }
                             acc = 1;
                         }
@@ -313,7 +376,16 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         long long t_wait = 0, t_work = 0;
         long long tprof[4] = {0, 0, 0, 0};
         int it_par = 0;
+        using tau_t = std::conditional_t<I8, int, float>;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
+        tau_t TAU_LO, TAU_HI;  // "nothing seen yet" / "row does not exist"
+        if constexpr (I8) {
+            TAU_LO = (int)0x80000000;
+            TAU_HI = 0x7fffffff;
+        } else {
+            TAU_LO = NEG_INF;
+            TAU_HI = POS_INF;
+        }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ItemInfo it = decode_item(args, item);
             const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
@@ -325,7 +397,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
                                       : 0;
             key64_t *list = args.cand + slot * GCAP;
-            float tau = valid ? NEG_INF : POS_INF;
+            tau_t tau = valid ? TAU_LO : TAU_HI;
             int cnt = 0;
             long long b_hi = (long long)t_hi * TC_BN;
             if (b_hi > args.nb) b_hi = args.nb;
@@ -334,8 +406,12 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             int t0 = 0;
             for (int i = 0; i < t_hi - t_lo; ++i) {
                 const long long tw0 = PROF ? clock64() : 0;
-                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
-                                                 cnt, list, ctr);
+                if constexpr (I8)
+                    wait_acc_with_idle_shrinks_i32<GCAP>(&tail.acc_full[as], acc_ph, L, lane, tau,
+                                                         cnt, list);
+                else
+                    wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr,
+                                                     tau, cnt, list, ctr);
                 const long long tw1 = PROF ? clock64() : 0;
                 t_wait += tw1 - tw0;
                 ptx::tc_fence_after_sync();
@@ -354,12 +430,20 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
                 };
-                if (args.debug_mode != 1)
-                    filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
-                                      args.debug_mode, nullptr, tau, cnt, list, ctr, release,
-                                      args.debug_mode == 9 ? tprof : nullptr);
-                else
-                    release();
+                if constexpr (I8) {
+                    if (args.debug_mode != 1)
+                        filter_tile_i32<GCAP>(tbase, tile0, special, ib_hi, self, L, lane, tau, cnt,
+                                              list, release);
+                    else
+                        release();
+                } else {
+                    if (args.debug_mode != 1)
+                        filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
+                                          args.debug_mode, nullptr, tau, cnt, list, ctr, release,
+                                          args.debug_mode == 9 ? tprof : nullptr);
+                    else
+                        release();
+                }
                 ctr[3] += TC_BN / 32;
                 if (PROF) t_work += clock64() - tw1;
                 as ^= 1;
@@ -368,7 +452,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             it_par ^= 1;
             if (valid) {
                 args.cand_cnt[slot] = cnt;
-                args.cand_tau[slot] = tau;
+                if constexpr (I8)  // |score| < 2^24: exact as a float; "no threshold" = -inf
+                    args.cand_tau[slot] = tau == TAU_LO ? NEG_INF : (float)tau;
+                else
+                    args.cand_tau[slot] = tau;
             }
         }
         if (PROF && lane == 0) {
@@ -644,6 +731,7 @@ struct RerankArgs {
     int check_eps;          // debug: measure |S'_tensor - S'_fp64| / eps over all candidates
     const PrepScalars *sc;
     int ksteps;             // UMMA K steps per accumulator (for the accumulation bound)
+    int i8;                 // scores came from the integer path (knn_tc_i8.cuh)
     int *assign;
     float *dis;
     int *fb_rows;           // absolute query ids of rows that failed the certificate
@@ -690,7 +778,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         eps += (double)a.ksteps * (1.0 / 4194304.0) * (xn * ymax + 0.5 * ymax * ymax);
         eps += ymax * ymax * (1.0 / 536870912.0);
     }
-    if (a.check_eps) {
+    if (a.check_eps && !a.i8) {
         // debug: the bound must dominate the real error of every score the kernel produced
         float worst = 0.0f;
         for (int i = lane; i < n; i += 32) {
@@ -745,8 +833,18 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
             ok = false;  // cannot happen (a threshold implies >= L >= kcap candidates)
         } else {
             const double gamma = (double)(a.d + 2) * (1.0 / 16777216.0) * 1.0001;
-            const double lb =
-                (xn2 * (1.0 - 1e-12) - 2.0 * ((double)tau + eps) / (sigma * sigma)) * (1.0 - gamma);
+            double lb;
+            if (a.i8) {
+                // tau is an exact integer score T = x.y' - ceil(|y|^2/2); a non-candidate has
+                // dist = |x|^2 - 256 sum(x) - 2 T - {0,1} >= |x|^2 - 256 sum(x) - 2 tau - 1
+                double x1 = 0.0;
+                for (int i = lane; i < a.d; i += 32) x1 += (double)qrow[i];
+                for (int o = 16; o > 0; o >>= 1) x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+                lb = (xn2 - 256.0 * x1 - 2.0 * (double)tau - 1.0) * (1.0 - gamma);
+            } else {
+                lb = (xn2 * (1.0 - 1e-12) - 2.0 * ((double)tau + eps) / (sigma * sigma)) *
+                     (1.0 - gamma);
+            }
             const double dk = (double)key_score(keys[a.kcap - 1]);
             ok = lb > dk;
         }
@@ -891,6 +989,8 @@ size_t tc_smem_bytes(const TcPlan &p) {
 
 struct TcLayout {
     size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
+    size_t a8;  // integer path: u8 query operand [n_rows x d32] (0 when the path is disabled)
+    int d32;
     // second pass (rows that failed the first certificate, redone with longer lists)
     size_t p2_q, p2_xh, p2_norm, p2_cand, p2_cnt, p2_tau, p2_fb;
     int p2_rows;  // rows per second-pass batch
@@ -935,6 +1035,14 @@ int tc_pick_variant(int d16, int gcap) {
 }
 
 constexpr int P2_GCAP = 512, P2_MAX_LISTS = 4;
+
+// Integer path for data made of integers in [0, 255] (knn_tc_i8.cuh): taken whenever the data
+// qualifies; $PQH_TC_I8=0 keeps such data on the FP16 path (A/B measurements, tests of the FP16
+// error bound).  Read on every call so that one process can compare both.
+bool i8_enabled() {
+    const char *e = getenv("PQH_TC_I8");
+    return e ? atoi(e) != 0 : true;
+}
 
 void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join, int num_sms,
                TcLayout *lo, int L_override = 0) {
@@ -1007,6 +1115,8 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     lo->cnt = take(lo->n_slots * sizeof(int));
     lo->tau = take(lo->n_slots * sizeof(float));
     lo->fb_rows = take((size_t)n_rows * sizeof(int));
+    lo->d32 = (d + 31) / 32 * 32;
+    lo->a8 = i8_enabled() ? take((size_t)n_rows * lo->d32) : 0;
     {
         int p2 = n_rows / 16;
         if (p2 < 2048) p2 = 2048;
@@ -1074,28 +1184,56 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     if (ev) cudaEventRecord(ev[0], stream);
     if ((e = cudaMemsetAsync(sc, 0, sizeof(PrepScalars), stream)) != cudaSuccess) return e;
 
-    // ---- prep ----
     // queries of this launch: rows [q_src0, q_src0 + n_rows) of d_queries
     const int q_src0 = self_join ? q_begin : q_begin - q_row0;
-    const int grid_ma = num_sms * 8;
-    maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_base, (size_t)nb * d, &sc->maxabs_bits);
-    ++*launches;
-    if (!self_join) {
-        maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
-                                                   (size_t)n_rows * d, &sc->maxabs_bits);
-        ++*launches;
+    const char *dbg_env = getenv("PQH_TC_DEBUG");
+    const int debug_mode = dbg_env ? atoi(dbg_env) : 0;
+
+    // ---- prep, integer flavour (opt-in): tried first, kept only if every value qualifies ----
+    bool used_i8 = false;
+    uint8_t *a8 = reinterpret_cast<uint8_t *>(w + lo.a8);
+    if (i8_enabled() && lo.variant == 1 && debug_mode == 0 &&
+        resident_fits(1, lo.d32 / 2, lo.gcap)) {
+        const float *qsrc = (self_join ? d_base : d_queries) + (size_t)q_src0 * d;
+        prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(
+            d_base, nb, d, lo.d32, reinterpret_cast<uint8_t *>(xh_b), norm_b,
+            reinterpret_cast<int8_t *>(fold_b), 1, sc);
+        prep_rows_i8_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(
+            qsrc, n_rows, d, lo.d32, a8, self_join ? nullptr : norm_q, nullptr, 0, sc);
+        fold_const_i8_kernel<<<(TC_ROWS * 32 + 255) / 256, 256, 0, stream>>>(
+            reinterpret_cast<uint8_t *>(fold_a));
+        *launches += 3;
+        PrepScalars probe;
+        if ((e = cudaMemcpyAsync(&probe, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost,
+                                 stream)) != cudaSuccess)
+            return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        used_i8 = probe.pad[2] == 0;
     }
-    prep_rows_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d16, xh_b, norm_b, fold_b,
-                                                       1, sc);
-    ++*launches;
-    if (!self_join) {
-        prep_rows_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
-                                                               n_rows, d, lo.d16, xh_q, norm_q,
-                                                               nullptr, 0, sc);
+
+    // ---- prep, FP16 flavour ----
+    auto prep_fp16 = [&]() {
+        const int grid_ma = num_sms * 8;
+        maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_base, (size_t)nb * d, &sc->maxabs_bits);
         ++*launches;
-    }
-    fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
-    ++*launches;
+        if (!self_join) {
+            maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
+                                                       (size_t)n_rows * d, &sc->maxabs_bits);
+            ++*launches;
+        }
+        prep_rows_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d16, xh_b, norm_b,
+                                                           fold_b, 1, sc);
+        ++*launches;
+        if (!self_join) {
+            prep_rows_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
+                                                                   n_rows, d, lo.d16, xh_q, norm_q,
+                                                                   nullptr, 0, sc);
+            ++*launches;
+        }
+        fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
+        ++*launches;
+    };
+    if (!used_i8) prep_fp16();
 
     // ---- one pass = tensor-core kernel + re-rank over a set of query rows ----
     struct Pass {
@@ -1113,23 +1251,24 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         float *tau;
         int *fb_rows;
         uint32_t *fb_count;
+        bool i8;                 // integer operands (first pass only)
+        const void *b_op;        // base operand rows
+        int op_cols;             // operand row length in 2-byte units (the tensor maps' view)
     };
-    const char *dbg_env = getenv("PQH_TC_DEBUG");
-    const int debug_mode = dbg_env ? atoi(dbg_env) : 0;
     auto run_pass = [&](const Pass &p) -> cudaError_t {
         const TcLayout &pl = *p.lo;
         TcMaps maps;
         TcArgs args;
-        if (!build_plan(pl.d16, &args.plan) && pl.variant != 4) return cudaErrorInvalidValue;
+        if (!build_plan(p.op_cols, &args.plan) && pl.variant != 4) return cudaErrorInvalidValue;
         const uint32_t boxc[3] = {64, 32, 16};
         const uint32_t a_box_rows = pl.variant == 2 ? 128 : TC_ROWS;
         const uint32_t b_box_rows =
             pl.variant == 3 ? 64 : (pl.variant == 5 ? tc5_tile_rows() : TC_BN);
         for (int c = 0; c < 3; ++c) {
             // classes a small d never uses still need a legal box
-            const uint32_t bc = boxc[c] <= (uint32_t)pl.d16 ? boxc[c] : 16;
-            if (!make_map(&maps.a[c], p.xh_q, p.a_rows, pl.d16, bc, a_box_rows) ||
-                !make_map(&maps.b[c], xh_b, nb, pl.d16, bc, b_box_rows))
+            const uint32_t bc = boxc[c] <= (uint32_t)p.op_cols ? boxc[c] : 16;
+            if (!make_map(&maps.a[c], p.xh_q, p.a_rows, p.op_cols, bc, a_box_rows) ||
+                !make_map(&maps.b[c], p.b_op, nb, p.op_cols, bc, b_box_rows))
                 return cudaErrorInvalidValue;
         }
         if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, a_box_rows) ||
@@ -1195,13 +1334,18 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             // the PROF instantiations carry the clock64()/counter instrumentation (PQH_TC_DEBUG)
             if (debug_mode != 0) {
                 if (pl.gcap == 256)
-                    LAUNCH_TC((knn_tc_kernel<256, true>), tc_smem_bytes<256>(args.plan), grid);
+                    LAUNCH_TC((knn_tc_kernel<256, true, false>), tc_smem_bytes<256>(args.plan), grid);
                 else
-                    LAUNCH_TC((knn_tc_kernel<512, true>), tc_smem_bytes<512>(args.plan), grid);
+                    LAUNCH_TC((knn_tc_kernel<512, true, false>), tc_smem_bytes<512>(args.plan), grid);
+            } else if (p.i8) {
+                if (pl.gcap == 256)
+                    LAUNCH_TC((knn_tc_kernel<256, false, true>), tc_smem_bytes<256>(args.plan), grid);
+                else
+                    LAUNCH_TC((knn_tc_kernel<512, false, true>), tc_smem_bytes<512>(args.plan), grid);
             } else if (pl.gcap == 256) {
-                LAUNCH_TC((knn_tc_kernel<256, false>), tc_smem_bytes<256>(args.plan), grid);
+                LAUNCH_TC((knn_tc_kernel<256, false, false>), tc_smem_bytes<256>(args.plan), grid);
             } else {
-                LAUNCH_TC((knn_tc_kernel<512, false>), tc_smem_bytes<512>(args.plan), grid);
+                LAUNCH_TC((knn_tc_kernel<512, false, false>), tc_smem_bytes<512>(args.plan), grid);
             }
         }
 #undef LAUNCH_TC
@@ -1235,6 +1379,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         ra.check_eps = getenv("PQH_TC_CHECK_EPS") ? 1 : 0;
         ra.sc = sc;
         ra.ksteps = (pl.d16 + FOLD_COLS) / 16;
+        ra.i8 = p.i8 ? 1 : 0;
         ra.assign = d_assign;
         ra.dis = d_dis;
         ra.fb_rows = p.fb_rows;
@@ -1264,9 +1409,12 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     if (ev) cudaEventRecord(ev[1], stream);
     Pass p1;
     p1.lo = &lo;
-    p1.xh_q = xh_q;
-    p1.a_rows = self_join ? (uint64_t)nb : (uint64_t)n_rows;
-    p1.q_op_begin = self_join ? q_begin : 0;
+    p1.i8 = used_i8;
+    p1.b_op = xh_b;
+    p1.op_cols = used_i8 ? lo.d32 / 2 : lo.d16;
+    p1.xh_q = used_i8 ? reinterpret_cast<const __half *>(a8) : xh_q;
+    p1.a_rows = (self_join && !used_i8) ? (uint64_t)nb : (uint64_t)n_rows;
+    p1.q_op_begin = (self_join && !used_i8) ? q_begin : 0;
     p1.q_mat = self_join ? d_base : d_queries;
     p1.q_row_begin = q_src0;
     p1.qnorm64 = self_join ? norm_b : norm_q - q_src0;  // indexed by q_row_begin + r
@@ -1298,6 +1446,12 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         int L2 = 4 * L1;
         if (L2 > 192) L2 = 192;
         if (L2 > L1) {
+            if (used_i8) {  // the second pass runs on FP16 operands: build them now
+                if ((e = cudaMemsetAsync(&sc->maxabs_bits, 0, 3 * sizeof(uint32_t), stream)) !=
+                    cudaSuccess)
+                    return e;
+                prep_fp16();
+            }
             float *q2 = reinterpret_cast<float *>(w + lo.p2_q);
             __half *xh2 = reinterpret_cast<__half *>(w + lo.p2_xh);
             double *norm2 = reinterpret_cast<double *>(w + lo.p2_norm);
@@ -1335,6 +1489,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                 p2.tau = reinterpret_cast<float *>(w + lo.p2_tau);
                 p2.fb_rows = fb2;
                 p2.fb_count = fb2_count;
+                p2.i8 = false;
+                p2.b_op = xh_b;
+                p2.op_cols = lo.d16;
                 if ((e = run_pass(p2)) != cudaSuccess) return e;
             }
             if ((e = cudaMemcpyAsync(&hsc, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost,
@@ -1350,7 +1507,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     if (times) {
         times->candidates = 0;
         for (int i = 0; i < 32; ++i) times->candidates += (double)hsc.cand_total[i];
-        times->inexact = (int)hsc.inexact;
+        times->inexact = used_i8 ? 2 : (int)hsc.inexact;
         {
             union { uint32_t u; float f; } cv;
             cv.u = hsc.pad[0];

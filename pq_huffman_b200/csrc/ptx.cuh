@@ -135,6 +135,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with 8-bit integer operands (K = 32 per instruction) and an s32 accumulator
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread are complete
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile(
@@ -300,6 +313,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
            | (0u << 15) | (0u << 16)     // A, B K-major
            | ((uint32_t)(N >> 3) << 17)  // N / 8
            | ((uint32_t)(M >> 4) << 24); // M / 16
+}
+
+// kind::i8: A unsigned 8-bit, B signed 8-bit, D s32 (cute/arch/mma_sm100_desc.hpp: c_format 2,
+// a/b_format 0 = unsigned, 1 = signed)
+__host__ __device__ constexpr uint32_t make_idesc_i8_u8s8(int M, int N) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | (0u << 15) | (0u << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // three-input max (sm_100: one FMNMX3)

@@ -131,6 +131,7 @@ def test_certificate_error_bound_dominates_real_error(monkeypatch, gen, n, d, k)
     core's FP32 accumulation).  Measure the real error of every candidate score against an FP64
     dot product on the device and check that the bound holds with room to spare."""
     monkeypatch.setenv("PQH_TC_CHECK_EPS", "1")
+    monkeypatch.setenv("PQH_TC_I8", "0")    # this test is about the FP16 path, also for uint8 data
     x = {"sift": synth.sift_like, "gist": synth.gist_like, "deep": synth.deep_like,
          "uniform": synth.uniform}[gen](n, d, seed=7 * n + d)
     knn.knn_full_thread(x, None, k)
@@ -345,3 +346,36 @@ def test_resident_dataset_blocks_on_two_gpus_concurrently(oracle):
         knn.init([0])
     for ids, got in zip(blocks, out):
         assert_rows_equal(got, oracle.knn(x[ids], None, k))
+
+
+def test_integer_tensor_path(monkeypatch, oracle):
+    """uint8-valued data (SIFT-shaped) takes the exact INT8 tensor-core path (stats:
+    inexact_operands == 2), PQH_TC_I8=0 keeps it on the FP16 path; data the 8-bit operands or the
+    fold columns cannot hold falls back to FP16 by itself.  Same bits either way."""
+    x = synth.with_duplicates_and_ties(synth.sift_like(9000, 128, seed=31), n_dups=10, n_ties=10)
+    exp = oracle.knn(x, None, 17)
+    assert_rows_equal(knn.knn_full_thread(x, None, 17), exp)
+    assert knn.last_stats()["inexact_operands"] == 2
+    monkeypatch.setenv("PQH_TC_I8", "0")
+    assert_rows_equal(knn.knn_full_thread(x, None, 17), exp)
+    assert knn.last_stats()["inexact_operands"] == 0
+    monkeypatch.delenv("PQH_TC_I8")
+    # distinct queries, ragged sizes, odd dimension (padding to 32-byte K steps)
+    b = synth.sift_like(5000, 100, seed=32)
+    v = synth.sift_like(777, 100, seed=33)
+    assert_rows_equal(knn.knn_full_thread(b, v, 9), oracle.knn(b, v, 9))
+    assert knn.last_stats()["inexact_operands"] == 2
+    # |y|^2 beyond what the fold columns hold: bright rows
+    rng = np.random.default_rng(5)
+    bright = rng.integers(200, 256, size=(4000, 128)).astype(np.float32)
+    assert_rows_equal(knn.knn_full_thread(bright, None, 9), oracle.knn(bright, None, 9))
+    assert knn.last_stats()["inexact_operands"] == 0
+    # one non-integer value anywhere: the whole call stays on FP16
+    y = synth.sift_like(4000, 64, seed=34)
+    y[1234, 7] += 0.5
+    assert_rows_equal(knn.knn_full_thread(y, None, 9), oracle.knn(y, None, 9))
+    assert knn.last_stats()["inexact_operands"] in (0, 1)
+    z = synth.sift_like(4000, 64, seed=35)
+    z[17, 3] = -1.0
+    assert_rows_equal(knn.knn_full_thread(z, None, 9), oracle.knn(z, None, 9))
+    assert knn.last_stats()["inexact_operands"] in (0, 1)

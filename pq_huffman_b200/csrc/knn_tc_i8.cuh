@@ -6,7 +6,7 @@
 // (tcgen05.mma kind::i8, u8 x s8 -> s32, twice the FP16 rate):
 //     A (queries) = x as u8,  B (base) = y' = y - 128 as s8,
 //     32 extra K columns fold G(y) = ceil(|y|^2 / 2):  A side constants (255 x30, 1, 1),
-//     B side s8 digits b with sum(c_i b_i) = -G   (capacity: |y|^2 < 1.95e6),
+//     B side s8 digits b with sum(c_i b_i) = -G   (capacity: |y|^2 <= 1958398),
 //     accumulator T = x.y' - G,   dist = |x|^2 - 256 sum(x) - 2 T - (2G - |y|^2),  2G-|y|^2 in {0,1}.
 // Larger T == smaller distance within a row; the only slack the certificate needs is that 0/1.
 // The epilogue is the float one (knn_tc_common.cuh) with integer compares; candidate keys keep

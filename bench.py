@@ -11,9 +11,13 @@ evenly over the ranks and the per-rank neighbour lists are gathered to rank 0
 
   value      queries/s with the vectors already resident in HBM (device-timed,
              CUDA events, max over ranks)
-  e2e        queries/s through the host-pointer C ABI (pqh_knn_search_rows /
-             knn_full_thread): pinned host buffers, H2D + search + D2H inside the
-             timed region; for N > 1 also the NCCL broadcast and gather
+  e2e        queries/s through the host-pointer C ABI (pqh_knn_search_rows, what
+             knn_full_thread calls) with PAGEABLE host buffers, as the reference's caller
+             hands them over (compute_nn_fast.c:471-481): staged H2D + search + D2H inside
+             the timed region.  For N > 1 the same single call runs on rank 0 with the
+             library's own multi-GPU path (PQH_DEVICES = all N GPUs: every GPU uploads 1/N
+             of the base over its own link, one ncclAllGather over NVLink, query rows split
+             over the GPUs, results written straight into the caller's arrays)
   roofline   the tcgen05 distance-GEMM kernel against the measured dense bf16/fp16 peak
   cpu_baseline  the Yael-shaped CPU implementation (oracle/knn_blas.c) on a bounded
              sample of the same workload, on this box's host cores (N == 1 only)
@@ -114,6 +118,15 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def config_of(workload, gpus):
+    """The `config` object of the JSON line: the same keys and values for both arms."""
+    gen, n, d, num_nn = WORKLOADS[workload]
+    per = (n + gpus - 1) // gpus
+    return {"workload": DESCRIPTIONS[workload], "n": n, "d": d, "k": num_nn,
+            "rows_per_gpu": per, "parallelism": f"query-rows/{gpus}",
+            "l2": "inputs (%.0f MB) larger than L2, no flush needed" % (n * d * 4 / 1e6)}
+
+
 def make_data(workload):
     from pq_huffman_b200 import synth
     gen, n, d, num_nn = WORKLOADS[workload]
@@ -162,8 +175,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * n / qps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": DESCRIPTIONS[args.workload], "n": n, "d": d, "k": k - 1,
-                   "inputs": "host"},
+        "config": config_of(args.workload, args.gpus),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": sample,
                          "note": "Yael v438 is not vendored/installed; oracle/knn_blas.c restates "
@@ -190,8 +202,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # control-plane barriers that keep the GPUs free (an NCCL barrier spins on the device)
+        ctl = dist.new_group(backend="gloo")
     knn.init([local])
 
     gen, n, d, num_nn = WORKLOADS[args.workload]
@@ -200,11 +215,10 @@ def run_ours(args):
     rows = q_hi - q_lo
 
     # ---- data: rank 0 generates, pinned; the other ranks only receive the broadcast ----
-    host_x = None
+    host_x = x_np = None
     if rank == 0:
-        x_np, _ = make_data(args.workload)
+        x_np, _ = make_data(args.workload)           # plain numpy memory: pageable
         host_x = torch.from_numpy(x_np).pin_memory()
-        del x_np
     d_x = torch.empty((n, d), dtype=torch.float32, device=dev)
     if rank == 0:
         d_x.copy_(host_x, non_blocking=True)
@@ -255,48 +269,51 @@ def run_ours(args):
     ms_max, gemm_ms_max = float(t[0]), float(t[1])
     value = n * args.steps / (ms_max / 1e3)
 
-    # ---- end-to-end arm: host pointers through the C ABI ----
-    out_a = torch.empty((max(rows, 1), k), dtype=torch.int32).pin_memory()
-    out_d = torch.empty((max(rows, 1), k), dtype=torch.float32).pin_memory()
-    if world > 1 and rank == 0:
-        full_a = torch.empty((n, k), dtype=torch.int32).pin_memory()
-        full_d = torch.empty((n, k), dtype=torch.float32).pin_memory()
-
-    def e2e_step():
-        if world == 1:
-            # the call a user of the reference makes: host buffers in, host results out
-            import ctypes  # noqa: F401
-            lib_rows = knn._lib.load().pqh_knn_search_rows
-            rc = lib_rows(n, n, d, k, host_x.data_ptr(), host_x.data_ptr(), 1, 0, n,
-                          out_a.data_ptr(), out_d.data_ptr())
-            if rc:
-                raise RuntimeError(knn._lib.load().pqh_last_error().decode())
-        else:
-            with torch.cuda.stream(stream):
-                if rank == 0:
-                    d_x.copy_(host_x, non_blocking=True)        # H2D of this step's input
-                dist_knn.broadcast_base(d_x, src=0)             # base over NVLink (NCCL)
-                device_step()
-                ga, gd = dist_knn.gather_rows(d_assign, d_dis, n, k, dst=0)   # NCCL gather
-                if rank == 0:                                   # D2H of the step's result
-                    full_a.copy_(ga, non_blocking=True)
-                    full_d.copy_(gd, non_blocking=True)
+    # ---- MMA-only ceiling of the GEMM kernel (N == 1): same launch, filter switched off ----
+    mma_only_ms = None
+    if world == 1 and not args.no_ceiling:
+        os.environ["PQH_TC_DEBUG"] = "1"
+        knn.init([local])
+        vals = []
+        for _ in range(3):
+            device_step()
             torch.cuda.synchronize()
+            vals.append(knn.last_stats()["ms_gemm"])
+        mma_only_ms = min(vals[1:])
+        del os.environ["PQH_TC_DEBUG"]
+        knn.init([local])
 
+    # ---- end-to-end arm: pageable host pointers through the C ABI, on rank 0 ----
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * e2e_steps / float(te[0])
-    e2e_stats = knn.last_stats() if world == 1 else None
+    e2e_s, e2e_stats = 0.0, None
+    if ctl is not None:
+        torch.cuda.synchronize()
+        dist.barrier(group=ctl)
+    if rank == 0:
+        del host_x
+        knn.init(list(range(world)))      # the library's own multi-GPU context (NCCL inside)
+        out_a = np.empty((n, k), dtype=np.int32)
+        out_d = np.empty((n, k), dtype=np.float32)
+        lib = knn._lib.load()
+
+        def e2e_step():
+            # the call a user of the reference makes: host buffers in, host results out
+            rc = lib.pqh_knn_search_rows(n, n, d, k, x_np.ctypes.data, x_np.ctypes.data, 1, 0, n,
+                                         out_a.ctypes.data, out_d.ctypes.data)
+            if rc:
+                raise RuntimeError(lib.pqh_last_error().decode())
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_s = time.perf_counter() - t0
+        e2e_stats = knn.last_stats()
+        assert out_a[n // 2, 0] == n // 2 and e2e_stats["rows"] == n
+    if ctl is not None:
+        dist.barrier(group=ctl)
+    e2e_value = n * e2e_steps / e2e_s if rank == 0 else 0.0
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -324,20 +341,25 @@ def run_ours(args):
                       "f32 (results: exact FP32 re-rank; candidate filter: f16 tensor cores, "
                       "f32 accumulate)"),
             "data": "synthetic",
-            "config": {"workload": DESCRIPTIONS[args.workload], "n": n, "d": d, "k": num_nn,
-                       "rows_per_gpu": per, "parallelism": f"query-rows/{world}",
-                       "l2": "inputs (%.0f MB) larger than L2, no flush needed" % (n * d * 4 / 1e6)},
+            "config": config_of(args.workload, world),
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": n * d * 4,
                     "d2h_bytes_per_step": n * k * 8, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * float(te[0]) / e2e_steps,
-                    "api": "pqh_knn_search_rows (host pointers, pinned)" if world == 1 else
-                           "H2D + NCCL broadcast + pqh_knn_search_device + NCCL gather + D2H"},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "buffers": "pageable",
+                    "api": "pqh_knn_search_rows (host pointers)" if world == 1 else
+                           f"pqh_knn_search_rows on rank 0, library context over {world} GPUs: "
+                           "split H2D + ncclAllGather + per-GPU search + D2H into the caller's "
+                           "arrays"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": f"{peak_src} bf16_tflops_sustained (kernel runs inside a "
                                         "long step)",
                          "ms_per_launch": gemm_ms_max / launches_gemm, "traffic": traffic,
+                         # the same launch with the filter epilogue switched off: what the MMA
+                         # pipeline alone takes here (operand format and clocks included)
+                         "ms_mma_only": mma_only_ms,
+                         "frac_of_mma_only": (mma_only_ms / (gemm_ms_max / launches_gemm)
+                                              if mma_only_ms else None),
                          "operands": operands,
                          # the contract's denominator stays the measured bf16 peak; the INT8
                          # pipe's own nominal dense peak on B200 is twice the 16-bit one
@@ -355,7 +377,7 @@ def run_ours(args):
                                         ("ms_h2d", "ms_kernels", "ms_d2h", "ms_total")}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            qps, srows, dt = cpu_sample(host_x.numpy(), k, args.cpu_seconds, threads)
+            qps, srows, dt = cpu_sample(x_np, k, args.cpu_seconds, threads)
             line["cpu_baseline"] = {
                 "value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                 "sample": f"{srows} query rows x full {n}-row base in {dt:.1f} s "
@@ -394,6 +416,7 @@ def main():
     ap.add_argument("--workload", default="sift1m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ceiling", action="store_true", help="skip the MMA-only ceiling runs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     claim_stdout()

@@ -177,6 +177,15 @@ typedef struct pqh_knn_stats {
 } pqh_knn_stats_t;
 int pqh_knn_last_stats(pqh_knn_stats_t *out);
 
+/*
+ * Test hook: the rows of the last host-pointer search (absolute query ids) that the first
+ * tensor-core pass could not certify and that were therefore redone by the second pass or the
+ * exact kernel.  Copies at most `capacity` ids to `rows` and returns how many there were (at
+ * most 2^20 are remembered).  The full-size parity tests check every one of them against the
+ * oracle.
+ */
+int pqh_knn_last_fallback_rows(int *rows, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

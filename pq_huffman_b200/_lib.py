@@ -18,6 +18,7 @@ EXPORTS = (
     "pqh_knn_workspace_bytes",
     "pqh_knn_search_device",
     "pqh_knn_last_stats",
+    "pqh_knn_last_fallback_rows",
     "pqh_knn_dataset_load",
     "pqh_knn_dataset_search_block",
     "pqh_knn_dataset_release",
@@ -89,6 +90,8 @@ def load():
     lib.pqh_knn_search_device.restype = C.c_int
     lib.pqh_knn_last_stats.argtypes = [C.POINTER(Stats)]
     lib.pqh_knn_last_stats.restype = C.c_int
+    lib.pqh_knn_last_fallback_rows.argtypes = [vp, C.c_int]
+    lib.pqh_knn_last_fallback_rows.restype = C.c_int
     lib.pqh_knn_dataset_load.argtypes = [C.c_int, C.c_int, vp, C.c_longlong]
     lib.pqh_knn_dataset_load.restype = C.c_int
     lib.pqh_knn_dataset_search_block.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, vp]

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include <vector>
+
 namespace pqh {
 
 // ---- knn_exact.cu ----------------------------------------------------------
@@ -23,28 +25,44 @@ struct TcTimes {
     int inexact = 0;
     long long rows_pass2 = 0;   // rows redone by the second tensor-core pass
     float eps_ratio_max = 0.f;  // PQH_TC_CHECK_EPS: max |S'_tensor - S'_fp64| / eps
+    int slices = 0;             // row slices the first pass was cut into
+    // absolute ids of the rows the first pass did not certify (redone by the second pass or
+    // the exact kernel); at most 2^20 are kept -- a test hook (pqh_knn_last_fallback_rows)
+    std::vector<int> pass1_failed;
 };
+// The PQH_TC_* environment knobs are read once, when the device context is created
+// (pqh_knn_init / first search); tc_reload_env() is that read.
+void tc_reload_env();
 bool tc_supported(int n_rows, int nb, int d, int k, int self_join);
 size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms);
 cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row0, int q_begin,
                           int out_q_begin, int n_rows, int nb, int d, int k, int self_join,
                           int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
                           int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
-                          unsigned *h_fb_count, cudaEvent_t *ev, TcTimes *times);
+                          unsigned *h_fb_count, TcTimes *times);
 
-// ---- knn_tc3.cu (CTA-pair kernel; plan/maps/args are the structs of knn_tc_common.cuh) ----
-int tc3_pick_nstage(const void *plan);
-cudaError_t launch_tc3(const void *maps, const void *args, int gcap, int n_items, int num_sms,
-                       cudaStream_t stream);
-
-// ---- knn_tc5.cu (query operand in tensor memory) ----
-int tc5_tile_rows();
-int tc5_pick_nstage(const void *plan, int d16);
-cudaError_t launch_tc5(const void *maps, const void *args, const void *xh_q, const void *fold_a,
-                       int gcap, int d16, int n_items, int num_sms, cudaStream_t stream);
+// ---- knn_order.cu (locality order of the sweep) ----
+struct OrderOut {
+    const int *base_perm;  // operand row p of the base = data row base_perm[p]
+    const int *base_inv;   // inverse
+    const int *q_perm;     // query row r of the slice = absolute query id q_perm[r]
+    const int *q_self;     // self-join: position of query r's own vector in the permuted base
+    const int *qt_start;   // first base tile of the sweep of each query tile
+};
+int order_num_cells(int nb);
+size_t order_workspace_bytes(int slice_rows, int nb, int slice_qtiles);
+cudaError_t launch_order_base(const float *d_base, int nb, int d, int slice_rows_max,
+                              int slice_qtiles_max, void *d_work, cudaStream_t stream,
+                              int *launches, OrderOut *out);
+cudaError_t launch_order_queries(const float *d_queries, int q_begin, int n_rows, int nb, int d,
+                                 int self_join, int n_qtiles, int slice_rows_max,
+                                 int slice_qtiles_max, void *d_work, cudaStream_t stream,
+                                 int *launches, OrderOut *out);
+cudaError_t launch_order_self_of(const int *d_ids, int n, const int *base_inv, int *d_q_self,
+                                 cudaStream_t stream, int *launches);
 
 // ---- knn_tcs.cu (streaming kernel for large d) ----
 cudaError_t launch_tcs(const void *maps, const void *args, int gcap, int d16, int n_items,
-                       int num_sms, cudaStream_t stream);
+                       int num_sms, int nepi, cudaStream_t stream);
 
 }  // namespace pqh

@@ -11,10 +11,12 @@
 //   * the GEMM K dimension is [x'(d16) | fold(16)]: the A (query) side holds the
 //     constants (4096, 2, 2^-10, 0..), the B (base) side (-q1,-q2,-q3, 0..), so
 //     the accumulator IS S' and the epilogue is a bare threshold compare.
+// Data made of integers in [0, 255] takes the integer flavour instead (u8 x s8 -> s32 on
+// tcgen05.mma kind::i8, exact scores; knn_tc_common.cuh).
 // Nothing of the nq x nb score matrix reaches HBM: an epilogue thread owns one
 // query row, copies its 128 accumulator columns from TMEM to registers
 // (tcgen05.ld), reduces them to group maxima and only touches memory for the
-// rare elements above the row's running threshold (filter_tile_n in
+// rare elements above the row's running threshold (filter_tile in
 // knn_tc_common.cuh).
 //
 // Exactness.  Candidates (a superset of the top-L by S') are re-ranked by
@@ -26,28 +28,51 @@
 // (knn_exact.cu).  So the result is always the oracle's, and the tensor cores
 // only decide how fast it is found.
 //
-// Kernels in this file: knn_tc_kernel (default for d <= ~144: query tile
-// resident in shared memory), knn_tc2_kernel (CTA-pair experiment), the prep,
-// gather and re-rank kernels, and the host-side orchestration launch_knn_tc.
-// knn_tcs.cu holds the streaming kernel for larger d; knn_tc3.cu / knn_tc5.cu
-// two further measured experiments (profiles/README.md).
+// Kernels in this file: the prep kernels, knn_tc_kernel (d <= ~144: query tile resident in
+// shared memory), the re-rank kernel, and the host-side orchestration launch_knn_tc.
+// knn_tcs.cu holds the streaming kernel for larger d, knn_order.cu the locality order.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 #include "knn_tc_common.cuh"
-#include "knn_tc_i8.cuh"
-
-#include <type_traits>
 
 namespace pqh {
 
 namespace {
+
+// ------------------------------------------------------------------------------------
+// environment knobs, read once per context (tc_reload_env)
+struct TcEnv {
+    int i8 = 1;        // PQH_TC_I8: integer tensor-core path for uint8-valued data
+    int order = 1;     // PQH_TC_ORDER: locality order of the sweep (knn_order.cu)
+    int nepi = 8;      // PQH_TC_EPI: filter warps per CTA, 8 or 16
+    int nmma = 1;      // PQH_TC_MMA: MMA-issuing threads per CTA, 1 or 2
+    int l_exact = 0, l_inexact = 0;  // PQH_TC_LEXACT / PQH_TC_LINEXACT: candidates kept per row
+    int gcap = 0;      // PQH_TC_GCAP: list capacity, 256 or 512
+    int nsplit = 0;    // PQH_TC_NSPLIT: base splits
+    int no_tail = 0, no_pass2 = 0, check_eps = 0;
+    int debug = 0;     // PQH_TC_DEBUG: 1 = MMA only, 2 = no slow path (timing experiments)
+    int streaming = 0; // PQH_TC_STREAM=1: streaming kernel for every d
+    int slice_mb = 2048;  // PQH_TC_SLICE_MB: candidate-list scratch per row slice
+    bool loaded = false;
+};
+TcEnv g_env;
+
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+const TcEnv &env() {
+    if (!g_env.loaded) tc_reload_env();
+    return g_env;
+}
 
 // ------------------------------------------------------------------------------------
 // prep 1: max |x| over a matrix (grid-stride, float4), atomicMax on the IEEE bits
@@ -71,16 +96,19 @@ __global__ void __launch_bounds__(256) maxabs_kernel(const float *__restrict__ x
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out_bits, __float_as_uint(m));
 }
 
-// prep 2: one warp per row: fp16 operand row, exact-ish FP64 squared norm, fold pieces
+// prep 2: one warp per operand row: fp16 operand row, exact-ish FP64 squared norm, fold pieces.
+// Operand row `row` is built from data row perm[row] - perm_off (perm null: row itself); the
+// norm is stored under the DATA row.
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float *__restrict__ x, int n, int d, int d16, __half *__restrict__ xh,
                  double *__restrict__ norm64, __half *__restrict__ fold, int write_fold,
-                 PrepScalars *__restrict__ sc) {
+                 const int *__restrict__ perm, int perm_off, PrepScalars *__restrict__ sc) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
+    const int src = perm ? perm[row] - perm_off : row;
     const float sigma = scale_from_maxabs_bits(sc->maxabs_bits);
-    const float *xr = x + (size_t)row * d;
+    const float *xr = x + (size_t)src * d;
     __half *hr = xh + (size_t)row * d16;
     double acc = 0.0;
     bool inexact = false;
@@ -94,7 +122,7 @@ prep_rows_kernel(const float *__restrict__ x, int n, int d, int d16, __half *__r
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (__any_sync(0xffffffffu, inexact) && lane == 0) atomicOr(&sc->inexact, 1u);
-    if (lane == 0 && norm64) norm64[row] = acc;
+    if (lane == 0 && norm64) norm64[src] = acc;
     if (write_fold) {
         // n' = sigma^2 |y|^2 / 2 = 4096 q1 + 2 q2 + 2^-10 q3 (+ residual)
         const double np = acc * (double)sigma * (double)sigma * 0.5;
@@ -139,20 +167,20 @@ __global__ void fold_const_kernel(__half *__restrict__ fa) {
     fa[i] = __float2half_rn(v);
 }
 
-// Integer path (knn_tc_i8.cuh), one warp per row: the row as 8-bit integers -- u8 x for the A
-// (query) operand, s8 x - 128 for the B (base) operand -- zero-padded to d32 bytes; FP64 squared
-// norm; for base rows the 32 s8 fold digits of G = ceil(|y|^2 / 2).  sc->pad[2] collects the
-// reasons the integer path cannot be used: bit 0 = a value is not an integer in [0, 255],
-// bit 1 = |y|^2 beyond the capacity of the fold columns.
+// Integer path, one warp per operand row: the row as 8-bit integers -- u8 x for the A (query)
+// operand, s8 x - 128 for the B (base) operand -- zero-padded to d32 bytes; FP64 squared norm
+// (stored under the data row); for base rows the 32 s8 fold digits of G = ceil(|y|^2 / 2).
+// sc->i8_reject collects the reasons the integer path cannot be used.  out == null: only check.
 __global__ void __launch_bounds__(256)
 prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t *__restrict__ out,
                     double *__restrict__ norm64, int8_t *__restrict__ fold, int as_base,
-                    PrepScalars *__restrict__ sc) {
+                    const int *__restrict__ perm, int perm_off, PrepScalars *__restrict__ sc) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
-    const float *xr = x + (size_t)row * d;
-    uint8_t *o = out + (size_t)row * d32;
+    const int src = perm ? perm[row] - perm_off : row;
+    const float *xr = x + (size_t)src * d;
+    uint8_t *o = out ? out + (size_t)row * d32 : nullptr;
     double acc = 0.0;
     bool bad = false;
     for (int i = lane; i < d32; i += 32) {
@@ -161,12 +189,12 @@ prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t 
         if (!(v >= 0.0f && v <= 255.0f) || (float)iv != v) bad = true;
         uint8_t b = 0;
         if (i < d) b = as_base ? (uint8_t)(int8_t)(iv - 128) : (uint8_t)iv;
-        o[i] = b;
+        if (o) o[i] = b;
         acc += (double)v * (double)v;
     }
     for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
     unsigned flags = __any_sync(0xffffffffu, bad) ? 1u : 0u;
-    if (norm64 && lane == 0) norm64[row] = acc;
+    if (norm64 && lane == 0) norm64[src] = acc;
     if (fold) {
         const long long G = ((long long)acc + 1) / 2;
         const long long q = G / I8_FOLD_UNIT;
@@ -182,7 +210,7 @@ prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t 
         }
         fold[(size_t)row * 32 + lane] = (int8_t)b;
     }
-    if (flags && lane == 0) atomicOr(&sc->pad[2], flags);
+    if (flags && lane == 0) atomicOr(&sc->i8_reject, flags);
 }
 
 __global__ void fold_const_i8_kernel(uint8_t *__restrict__ fa) {
@@ -194,19 +222,28 @@ __global__ void fold_const_i8_kernel(uint8_t *__restrict__ fa) {
 
 // ------------------------------------------------------------------------------------
 // main kernel
-template <int GCAP>
 struct TcSmemTail {
     uint64_t a_full, a_empty;
     uint64_t b_full[TC_NSTAGE], b_empty[TC_NSTAGE];
-    uint64_t acc_full[2], acc_empty[2];
-    uint32_t tmem_base;
-    int item_t0[2];  // first base tile of the current / next work item (set by the producer)
-    uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
+    EpiBars eb;
 };
 
-// I8: integer operands and scores (knn_tc_i8.cuh); everything else is shared.
-template <int GCAP, bool PROF, bool I8>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// both barriers of an MMA step probed together: their latencies overlap instead of adding up
+__device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *b1, uint32_t p1) {
+    const bool ok0 = ptx::mbar_try_wait(b0, p0);
+    const bool ok1 = ptx::mbar_try_wait(b1, p1);
+    if (!ok0) ptx::mbar_wait_slow(b0, p0);
+    if (!ok1) ptx::mbar_wait_slow(b1, p1);
+}
+
+// Warp roles: warp 0 = TMA producer, warps 1 .. NMMA = MMA issuers (one elected thread each),
+// then NEPI filter warps.  With NMMA == 2 the two issuers take alternate steps (issuer m fills
+// accumulator stage m), so the barrier round trips of one overlap the MMAs of the other.
+// Steps are numbered over the life of the CTA: B ring stage = step % 4, accumulator stage =
+// step & 1.
+template <int GCAP, bool I8, int NEPI, int NMMA>
+__global__ void __launch_bounds__(tc_threads(NEPI) + (NMMA - 1) * 32, 1)
+__maxnreg__(tc_max_regs(tc_threads(NEPI) + (NMMA - 1) * 32))
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -214,10 +251,11 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     const TcPlan &plan = args.plan;
     uint8_t *smA = smem;
     uint8_t *smB = smA + plan.a_bytes;
-    TcSmemTail<GCAP> &tail =
-        *reinterpret_cast<TcSmemTail<GCAP> *>(smB + TC_NSTAGE * plan.b_bytes);
+    TcSmemTail &tail = *reinterpret_cast<TcSmemTail *>(smB + TC_NSTAGE * plan.b_bytes);
+    uint64_t *tau_x = reinterpret_cast<uint64_t *>(&tail + 1);  // [256][2], NEPI == 16 only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EPI0 = 1 + NMMA;  // first filter warp
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 3; ++i) {
@@ -229,23 +267,23 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     }
     if (warp == 1 && lane == 0) {
         ptx::mbar_init(&tail.a_full, 1);
-        ptx::mbar_init(&tail.a_empty, 1);
+        ptx::mbar_init(&tail.a_empty, NMMA);
         for (int i = 0; i < TC_NSTAGE; ++i) {
             ptx::mbar_init(&tail.b_full[i], 1);
             ptx::mbar_init(&tail.b_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&tail.acc_full[i], 1);
-            ptx::mbar_init(&tail.acc_empty[i], TC_EPI_WARPS);
+            ptx::mbar_init(&tail.eb.acc_full[i], 1);
+            ptx::mbar_init(&tail.eb.acc_empty[i], 8);
         }
-        ptx::mbar_init(&tail.t0_ready, 1);
+        ptx::mbar_init(&tail.eb.t0_ready, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<512>(&tail.tmem_base);
+    if (warp == EPI0) ptx::tmem_alloc<512>(&tail.eb.tmem_base);
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
-    const uint32_t tmem_base = tail.tmem_base;
+    const uint32_t tmem_base = tail.eb.tmem_base;
 
     const int n_items = total_items(args);
 
@@ -258,10 +296,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 const ItemInfo it = decode_item(args, item);
                 const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
                 ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
-                const int t0 = item_start_tile(args.sc, t_lo, t_hi, my_next);
+                const int t0 = item_start_tile(args, qt, t_lo, t_hi, my_next);
                 my_next = t0;  // a full sweep ends where it started
-                tail.item_t0[it_par] = t0;
-                ptx::mbar_arrive(&tail.t0_ready);
+                tail.eb.item_t0[it_par] = t0;
+                ptx::mbar_arrive(&tail.eb.t0_ready);
                 ptx::mbar_arrive_expect_tx(&tail.a_full, plan.a_bytes);
                 for (int s = 0; s < plan.nseg; ++s) {
                     const TcSeg &sg = plan.seg[s];
@@ -275,7 +313,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 it_par ^= 1;
                 for (int i = 0; i < t_hi - t_lo; ++i) {
                     const int t = item_tile(i, t0, t_lo, t_hi);
-                    if ((i & 7) == 0) publish_cursor(args.sc, t);
+                    if ((i & 7) == 0) publish_cursor(args, t);
                     ptx::mbar_wait(&tail.b_empty[stage], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&tail.b_full[stage], plan.b_bytes);
                     uint8_t *dst = smB + stage * plan.b_bytes;
@@ -295,36 +333,37 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp < EPI0) {
+        // ===================== MMA issuer(s) =====================
         if (ptx::elect_one()) {
             constexpr uint32_t idesc =
                 I8 ? ptx::make_idesc_i8_u8s8(128, TC_BN) : ptx::make_idesc_f16(128, TC_BN);
-            int stage = 0, as = 0;
-            uint32_t ph = 0, acc_ph = 0, a_ph = 0;
-            long long mma_wait_b = 0, mma_wait_acc = 0;
-            const long long mma_t0 = PROF ? clock64() : 0;
+            const uint32_t m = (uint32_t)(warp - 1);
+            uint32_t gstep = 0, a_ph = 0;
+            long long t_wait = 0;
+            const bool prof = args.debug_mode != 0;
+            const long long t_begin = prof ? clock64() : 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ItemInfo it = decode_item(args, item);
-                const int t_lo = it.t_lo, t_hi = it.t_hi;
+                const int nst = it.t_hi - it.t_lo;
                 ptx::mbar_wait(&tail.a_full, a_ph);
                 a_ph ^= 1;
-                for (int i = 0; i < t_hi - t_lo; ++i) {
-                    const long long m0 = PROF ? clock64() : 0;
-                    ptx::mbar_wait(&tail.b_full[stage], ph);
-                    const long long m1 = PROF ? clock64() : 0;
-                    ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
-                    const long long m2 = PROF ? clock64() : 0;
-                    mma_wait_b += m1 - m0;
-                    mma_wait_acc += m2 - m1;
+                bool issued = false;
+                for (int i = (NMMA == 2) ? (int)((m ^ gstep) & 1u) : 0; i < nst; i += NMMA) {
+                    const uint32_t s = gstep + (uint32_t)i;
+                    const int stage = (int)(s % TC_NSTAGE), as = (int)(s & 1u);
+                    const uint32_t ph = (s / TC_NSTAGE) & 1u, acc_ph = (s >> 1) & 1u;
+                    const long long w0 = prof ? clock64() : 0;
+                    mbar_wait2(&tail.b_full[stage], ph, &tail.eb.acc_empty[as], acc_ph ^ 1);
+                    if (prof) t_wait += clock64() - w0;
                     ptx::tc_fence_after_sync();
                     const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
                     const uint32_t a_base = ptx::smem_u32(smA);
                     // The two query tiles are independent accumulation chains: alternate
                     // between them so that consecutive MMAs never depend on each other.
                     uint32_t acc = 0;
-                    for (int s = 0; s < plan.nseg; ++s) {
-                        const TcSeg &sg = plan.seg[s];
+                    for (int sgi = 0; sgi < plan.nseg; ++sgi) {
+                        const TcSeg &sg = plan.seg[sgi];
                         const uint32_t b_addr = b_base + sg.b_off;
                         const uint32_t sbo = 8 * sg.bytes, lay = seg_layout(sg.bytes);
                         for (int kk = 0; kk < sg.bytes / 32; ++kk) {
@@ -332,381 +371,37 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
 #pragma unroll
                             for (int g = 0; g < 2; ++g) {
                                 const uint32_t a_addr = a_base + sg.a_off + g * 128 * sg.bytes;
-                                if constexpr (I8)
-                                    ptx::umma_i8(tmem_base + (uint32_t)(as * 256 + g * 128),
-                                                 ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
-                                                 bd, idesc, acc);
-                                else
-                                    ptx::umma_f16(tmem_base + (uint32_t)(as * 256 + g * 128),
-                                                  ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
-                                                  bd, idesc, acc);
+                                const uint64_t ad = ptx::make_smem_desc(a_addr + kk * 32, sbo, lay);
+                                const uint32_t dcol = tmem_base + (uint32_t)(as * 256 + g * 128);
+                                if constexpr (I8) ptx::umma_i8(dcol, ad, bd, idesc, acc);
+                                else ptx::umma_f16(dcol, ad, bd, idesc, acc);
                             }
                             acc = 1;
                         }
                     }
                     ptx::umma_commit(&tail.b_empty[stage]);
-                    ptx::umma_commit(&tail.acc_full[as]);
-                    if (++stage == TC_NSTAGE) {
-                        stage = 0;
-                        ph ^= 1;
-                    }
-                    as ^= 1;
-                    if (as == 0) acc_ph ^= 1;
+                    ptx::umma_commit(&tail.eb.acc_full[as]);
+                    issued = true;
                 }
-                ptx::umma_commit(&tail.a_empty);
+                // the query tile may be overwritten once the MMAs of every issuer are done
+                if (issued) ptx::umma_commit(&tail.a_empty);
+                else ptx::mbar_arrive(&tail.a_empty);
+                gstep += (uint32_t)nst;
             }
-            if (PROF) {
-            PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
-            atomicAdd(&scw->dbg[6], (unsigned long long)mma_wait_b);
-            atomicAdd(&scw->dbg[7], (unsigned long long)mma_wait_acc);
-            atomicAdd(&scw->cand_total[63], (unsigned long long)(clock64() - mma_t0));
+            if (prof) {
+                PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
+                atomicAdd(&scw->dbg[0], (unsigned long long)t_wait);
+                atomicAdd(&scw->dbg[1], (unsigned long long)(clock64() - t_begin));
             }
         }
     } else {
         // ===================== epilogue: threshold filter =====================
-        const int e = warp - 2;
-        const int g = e >> 2;
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-        const int row_in_cta = g * 128 + quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
-        int as = 0;
-        uint32_t acc_ph = 0;
-        unsigned ctr[4] = {0, 0, 0, 0};
-        long long t_wait = 0, t_work = 0;
-        long long tprof[4] = {0, 0, 0, 0};
-        int it_par = 0;
-        using tau_t = std::conditional_t<I8, int, float>;
-        const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
-        tau_t TAU_LO, TAU_HI;  // "nothing seen yet" / "row does not exist"
-        if constexpr (I8) {
-            TAU_LO = (int)0x80000000;
-            TAU_HI = 0x7fffffff;
-        } else {
-            TAU_LO = NEG_INF;
-            TAU_HI = POS_INF;
-        }
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const ItemInfo it = decode_item(args, item);
-            const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
-            const int r = qt * TC_ROWS + row_in_cta;
-            const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join)
-                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
-                                 : -1;
-            const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
-                                      : 0;
-            key64_t *list = args.cand + slot * GCAP;
-            tau_t tau = valid ? TAU_LO : TAU_HI;
-            int cnt = 0;
-            long long b_hi = (long long)t_hi * TC_BN;
-            if (b_hi > args.nb) b_hi = args.nb;
-            const int ib_hi = (int)b_hi;
-
-            int t0 = 0;
-            for (int i = 0; i < t_hi - t_lo; ++i) {
-                const long long tw0 = PROF ? clock64() : 0;
-                if constexpr (I8)
-                    wait_acc_with_idle_shrinks_i32<GCAP>(&tail.acc_full[as], acc_ph, L, lane, tau,
-                                                         cnt, list);
-                else
-                    wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr,
-                                                     tau, cnt, list, ctr);
-                const long long tw1 = PROF ? clock64() : 0;
-                t_wait += tw1 - tw0;
-                ptx::tc_fence_after_sync();
-                if (i == 0) {
-                    ptx::mbar_wait(&tail.t0_ready, (uint32_t)it_par);
-                    t0 = *reinterpret_cast<volatile int *>(&tail.item_t0[it_par]);
-                }
-                const int t = item_tile(i, t0, t_lo, t_hi);
-                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
-                // id checks are only needed in the tile holding this row's own column and in
-                // the (possibly ragged) last tile
-                const int tile0 = t * TC_BN;
-                const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
-                auto release = [&]() {
-                    ptx::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
-                };
-                if constexpr (I8) {
-                    if (args.debug_mode != 1)
-                        filter_tile_i32<GCAP>(tbase, tile0, special, ib_hi, self, L, lane, tau, cnt,
-                                              list, release);
-                    else
-                        release();
-                } else {
-                    if (args.debug_mode != 1)
-                        filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
-                                          args.debug_mode, nullptr, tau, cnt, list, ctr, release,
-                                          args.debug_mode == 9 ? tprof : nullptr);
-                    else
-                        release();
-                }
-                ctr[3] += TC_BN / 32;
-                if (PROF) t_work += clock64() - tw1;
-                as ^= 1;
-                if (as == 0) acc_ph ^= 1;
-            }
-            it_par ^= 1;
-            if (valid) {
-                args.cand_cnt[slot] = cnt;
-                if constexpr (I8)  // |score| < 2^24: exact as a float; "no threshold" = -inf
-                    args.cand_tau[slot] = tau == TAU_LO ? NEG_INF : (float)tau;
-                else
-                    args.cand_tau[slot] = tau;
-            }
-        }
-        if (PROF && lane == 0) {
-            PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
-            for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
-            atomicAdd(&scw->dbg[4], (unsigned long long)t_wait);
-            atomicAdd(&scw->dbg[5], (unsigned long long)t_work);
-            if (args.debug_mode == 9)
-                for (int i = 0; i < 4; ++i)
-                    atomicAdd(&scw->cand_total[40 + i], (unsigned long long)tprof[i]);
-        }
+        epilogue_warps<GCAP, I8, NEPI>(args, warp - EPI0, warp & 3, lane, &tail.eb, tau_x);
     }
 
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
-}
-
-
-// ------------------------------------------------------------------------------------
-// Pair kernel: two CTAs of one cluster (one TPC) run tcgen05.mma.cta_group::2.  The pair owns
-// 256 query rows (each CTA: 128, its M half, A operand resident) and sweeps the base in tiles of
-// 256 rows; each CTA TMA-loads only ITS 128-row half of a base tile and the tensor cores of both
-// SMs consume both halves.  Versus the single-CTA kernel this halves the shared-memory operand
-// traffic per MMA (the single-CTA M=128,N=128 shape needs the full 128 B/cycle of shared memory
-// for operands alone) at the same L2 traffic per SM.
-// Synchronisation: "full" barriers live in the leader CTA (rank 0) and count the TMA bytes of
-// both CTAs; "empty"/"accumulator full" barriers are per CTA and are signalled by multicast
-// tcgen05.commit; "accumulator empty" lives in the leader and is arrived on remotely by the
-// epilogue warps of both CTAs.
-constexpr int TC2_NSTAGE = 4;
-
-template <int GCAP>
-struct Tc2SmemTail {
-    uint64_t a_full, a_empty;
-    uint64_t b_full[TC2_NSTAGE], b_empty[TC2_NSTAGE];
-    uint64_t acc_full[2], acc_empty[2];
-    uint32_t tau_shared[128];
-    uint32_t tmem_base;
-};
-
-template <int GCAP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-knn_tc2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const TcPlan &plan = args.plan;  // a_off/a_bytes are for 256 rows: this kernel uses half
-    const int a_bytes = plan.a_bytes / 2;
-    uint8_t *smA = smem;
-    uint8_t *smB = smA + a_bytes;
-    Tc2SmemTail<GCAP> &tail =
-        *reinterpret_cast<Tc2SmemTail<GCAP> *>(smB + TC2_NSTAGE * plan.b_bytes);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 3; ++i) {
-            ptx::prefetch_tmap(&maps.a[i]);
-            ptx::prefetch_tmap(&maps.b[i]);
-        }
-        ptx::prefetch_tmap(&maps.fa);
-        ptx::prefetch_tmap(&maps.fb);
-    }
-    if (warp == 1 && lane == 0) {
-        ptx::mbar_init(&tail.a_full, 1);
-        ptx::mbar_init(&tail.a_empty, 1);
-        for (int i = 0; i < TC2_NSTAGE; ++i) {
-            ptx::mbar_init(&tail.b_full[i], 1);
-            ptx::mbar_init(&tail.b_empty[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&tail.acc_full[i], 1);
-            ptx::mbar_init(&tail.acc_empty[i], 2 * 4);  // 4 filter warps in each CTA
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 2) ptx::tmem_alloc_2sm<512>(&tail.tmem_base);
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    ptx::cluster_sync_all();  // barriers of both CTAs initialised before any remote signal
-    ptx::tc_fence_after_sync();
-    const uint32_t tmem_base = tail.tmem_base;
-
-    const int n_items = args.n_qtiles * args.nsplit;
-
-    if (warp == 0) {
-        // ===================== TMA producer (both CTAs, own halves) =====================
-        if (ptx::elect_one()) {
-            const uint32_t a_full_l = ptx::mapa_u32(ptx::smem_u32(&tail.a_full), 0);
-            int stage = 0;
-            uint32_t ph = 0, a_ph = 0;
-            for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const int qt = item / args.nsplit, sp = item % args.nsplit;
-                int t_lo = sp * args.tiles_per_split;
-                int t_hi = t_lo + args.tiles_per_split;
-                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
-                ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
-                if (leader) ptx::mbar_arrive_expect_tx(&tail.a_full, 2 * a_bytes);
-                for (int s = 0; s < plan.nseg; ++s) {
-                    const TcSeg &sg = plan.seg[s];
-                    if (sg.fold)
-                        ptx::tma_load_2d_2sm(smA + sg.a_off / 2, &maps.fa, a_full_l, 0, 0);
-                    else
-                        ptx::tma_load_2d_2sm(smA + sg.a_off / 2, &maps.a[seg_class(sg.bytes)],
-                                             a_full_l, sg.k_off,
-                                             args.q_op_begin + qt * TC_ROWS + (int)rank * 128);
-                }
-                a_ph ^= 1;
-                for (int t = t_lo; t < t_hi; ++t) {
-                    ptx::mbar_wait(&tail.b_empty[stage], ph ^ 1);
-                    if (leader) ptx::mbar_arrive_expect_tx(&tail.b_full[stage], 2 * plan.b_bytes);
-                    const uint32_t b_full_l = ptx::mapa_u32(ptx::smem_u32(&tail.b_full[stage]), 0);
-                    uint8_t *dst = smB + stage * plan.b_bytes;
-                    const int row0 = t * 256 + (int)rank * 128;
-                    for (int s = 0; s < plan.nseg; ++s) {
-                        const TcSeg &sg = plan.seg[s];
-                        if (sg.fold)
-                            ptx::tma_load_2d_2sm(dst + sg.b_off, &maps.fb, b_full_l, 0, row0);
-                        else
-                            ptx::tma_load_2d_2sm(dst + sg.b_off, &maps.b[seg_class(sg.bytes)],
-                                                 b_full_l, sg.k_off, row0);
-                    }
-                    if (++stage == TC2_NSTAGE) {
-                        stage = 0;
-                        ph ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(256, 256);
-            int stage = 0, as = 0;
-            uint32_t ph = 0, acc_ph = 0, a_ph = 0;
-            for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const int sp = item % args.nsplit;
-                int t_lo = sp * args.tiles_per_split;
-                int t_hi = t_lo + args.tiles_per_split;
-                if (t_hi > args.n_btiles) t_hi = args.n_btiles;
-                ptx::mbar_wait(&tail.a_full, a_ph);
-                a_ph ^= 1;
-                for (int t = t_lo; t < t_hi; ++t) {
-                    ptx::mbar_wait(&tail.b_full[stage], ph);
-                    ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
-                    ptx::tc_fence_after_sync();
-                    const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
-                    const uint32_t a_base = ptx::smem_u32(smA);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-                    uint32_t acc = 0;
-                    for (int s = 0; s < plan.nseg; ++s) {
-                        const TcSeg &sg = plan.seg[s];
-                        const uint32_t a_addr = a_base + sg.a_off / 2;
-                        const uint32_t b_addr = b_base + sg.b_off;
-                        const uint32_t sbo = 8 * sg.bytes, lay = seg_layout(sg.bytes);
-                        for (int kk = 0; kk < sg.bytes / 32; ++kk) {
-                            ptx::umma_f16_2sm(d_tmem, ptx::make_smem_desc(a_addr + kk * 32, sbo, lay),
-                                              ptx::make_smem_desc(b_addr + kk * 32, sbo, lay), idesc,
-                                              acc);
-                            acc = 1;
-                        }
-                    }
-                    ptx::umma_commit_2sm(&tail.b_empty[stage]);
-                    ptx::umma_commit_2sm(&tail.acc_full[as]);
-                    if (++stage == TC2_NSTAGE) {
-                        stage = 0;
-                        ph ^= 1;
-                    }
-                    as ^= 1;
-                    if (as == 0) acc_ph ^= 1;
-                }
-                ptx::umma_commit_2sm(&tail.a_empty);
-            }
-        }
-    } else if (warp < 6) {
-        // ===================== epilogue: threshold filter =====================
-        // four filter warps (one per TMEM lane quadrant); a thread owns one query row and
-        // filters all 256 columns of a tile as two 128-column passes
-        const int quad = warp & 3;
-        const int row_in_cta = quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
-        uint32_t acc_empty_l[2];
-        acc_empty_l[0] = ptx::mapa_u32(ptx::smem_u32(&tail.acc_empty[0]), 0);
-        acc_empty_l[1] = ptx::mapa_u32(ptx::smem_u32(&tail.acc_empty[1]), 0);
-        int as = 0;
-        uint32_t acc_ph = 0;
-        unsigned ctr[4] = {0, 0, 0, 0};
-        const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
-        for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const int qt = item / args.nsplit, sp = item % args.nsplit;
-            int t_lo = sp * args.tiles_per_split;
-            int t_hi = t_lo + args.tiles_per_split;
-            if (t_hi > args.n_btiles) t_hi = args.n_btiles;
-            const int r = qt * TC_ROWS + (int)rank * 128 + row_in_cta;
-            const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join)
-                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
-                                 : -1;
-            const size_t slot = valid ? (size_t)r * args.nsplit + sp : 0;
-            key64_t *list = args.cand + slot * GCAP;
-            float tau = valid ? NEG_INF : POS_INF;
-            int cnt = 0;
-            long long b_hi = (long long)t_hi * 256;
-            if (b_hi > args.nb) b_hi = args.nb;
-            const int ib_hi = (int)b_hi;
-
-            for (int t = t_lo; t < t_hi; ++t) {
-                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
-                                                 cnt, list, ctr);
-                ptx::tc_fence_after_sync();
-                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256);
-                const int tile0 = t * 256;
-                const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + 256);
-                auto release = [&]() {
-                    ptx::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_l[as]);
-                };
-                auto keep = []() {};
-                if (args.debug_mode != 1) {
-                    filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane,
-                                      args.debug_mode, nullptr, tau, cnt, list, ctr, keep);
-                    filter_tile<GCAP>(tbase + 128, tile0 + 128, special, ib_hi, self, L, lane,
-                                      args.debug_mode, nullptr, tau, cnt, list, ctr, release);
-                } else {
-                    release();
-                }
-                ctr[3] += TC_BN / 32;
-                as ^= 1;
-                if (as == 0) acc_ph ^= 1;
-            }
-            if (valid) {
-                args.cand_cnt[slot] = cnt;
-                args.cand_tau[slot] = tau;
-            }
-        }
-        if (lane == 0) {
-            PrepScalars *scw = const_cast<PrepScalars *>(args.sc);
-            for (int i = 0; i < 4; ++i) atomicAdd(&scw->dbg[i], (unsigned long long)ctr[i]);
-        }
-    }
-
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    ptx::cluster_sync_all();  // the peer may still be signalling this CTA's barriers / TMEM
-    if (warp == 2) ptx::tmem_dealloc_2sm<512>(tmem_base);
+    if (warp == EPI0) ptx::tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------
@@ -715,23 +410,25 @@ constexpr int RR_WARPS = 4;
 
 struct RerankArgs {
     const float *base;
-    const float *queries;  // row r of this launch is queries[(q_row_begin + r) * d]
-    int q_row_begin;
-    int q_begin;           // absolute query index of row 0 (self-join id, output naming)
+    const float *queries;  // FP32 rows of this pass's queries: row ql (below) is the query's vector
+    int q_begin;           // absolute query index of row 0 when rows are in natural order
     const int *row_ids;    // second pass: absolute query index of every row instead
+    const int *q_perm;     // locality order: absolute query index of every row; the query's vector
+                           // is then row (q - q_begin) of `queries`
+    const int *base_perm;  // locality order: candidate position -> base row (null: identity)
     int out_q_begin;       // output row = q - out_q_begin
     int n_rows, nb, d, k, kcap, self_join;
-    int nlists, gcap;  // candidate lists per row (base splits), rows before the tail
-    int tail_row0, ns_tail;  // rows >= tail_row0 own ns_tail lists (knn_tc_common.cuh list_slot)
+    int nlists, gcap, npar;  // candidate lists per row = base splits x npar, capacity of one
+    int tail_row0, ns_tail;  // rows >= tail_row0 own ns_tail splits (knn_tc_common.cuh list_slot)
     const key64_t *cand;
     const int *cand_cnt;
     const float *cand_tau;
-    const double *qnorm64;  // |x|^2 of the query rows, indexed like queries (q_row_begin + r)
-    const double *bnorm64;  // |y|^2 of the base rows
+    const double *qnorm64;  // |x|^2 of the query rows, indexed like `queries`
+    const double *bnorm64;  // |y|^2 of the base rows (by base row)
     int check_eps;          // debug: measure |S'_tensor - S'_fp64| / eps over all candidates
     const PrepScalars *sc;
     int ksteps;             // UMMA K steps per accumulator (for the accumulation bound)
-    int i8;                 // scores came from the integer path (knn_tc_i8.cuh)
+    int i8;                 // scores came from the integer path
     int *assign;
     float *dis;
     int *fb_rows;           // absolute query ids of rows that failed the certificate
@@ -747,28 +444,41 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
                   (size_t)warp * a.d;
     const int r = blockIdx.x * RR_WARPS + warp;
     if (r >= a.n_rows) return;
-    const int q = a.row_ids ? a.row_ids[r] : a.q_begin + r;
+    const int q = a.q_perm ? a.q_perm[r] : (a.row_ids ? a.row_ids[r] : a.q_begin + r);
+    const int ql = a.q_perm ? q - a.q_begin : r;  // row of `queries` / `qnorm64`
 
-    // gather the candidate ids of all splits; tau = max over splits
-    int n = 0;
+    // the row's threshold: the largest over its lists (each is a statement about the whole row)
+    const int my_splits = r < a.tail_row0 ? a.nlists : a.ns_tail;
+    const size_t slot0 = list_slot(r, 0, a.tail_row0, a.nlists, a.ns_tail) * a.npar;
+    const int my_lists = my_splits * a.npar;
     float tau = __int_as_float(0xff800000);
-    const int my_lists = r < a.tail_row0 ? a.nlists : a.ns_tail;
+    for (int s = 0; s < my_lists; ++s) tau = fmaxf(tau, a.cand_tau[slot0 + s]);
+    // candidates scoring below it cannot be among the row's best L: drop them unseen
+    uint32_t hi_max = 0xffffffffu;
+    if (tau > __int_as_float(0xff800000))
+        hi_max = a.i8 ? i32_score_to_hi((int)tau) : float_to_ordered(-tau);
+    int n = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (int s = 0; s < my_lists; ++s) {
-        const size_t slot = list_slot(r, s, a.tail_row0, a.nlists, a.ns_tail);
-        const int c = a.cand_cnt[slot];
-        const key64_t *l = a.cand + slot * a.gcap;
-        for (int i = lane; i < c; i += 32) keys[n + i] = __ldcg(l + i);
-        n += c;
-        tau = fmaxf(tau, a.cand_tau[slot]);
+        const int c = a.cand_cnt[slot0 + s];
+        const key64_t *l = a.cand + (slot0 + s) * a.gcap;
+        for (int i0 = 0; i0 < c; i0 += 32) {
+            const int i = i0 + lane;
+            const key64_t kv = i < c ? __ldcg(l + i) : 0;
+            const bool keep = i < c && (uint32_t)(kv >> 32) <= hi_max;
+            const unsigned kb = __ballot_sync(0xffffffffu, keep);
+            if (keep) keys[n + __popc(kb & lt_mask)] = kv;
+            n += __popc(kb);
+        }
     }
-    const float *qsrc = a.queries + (size_t)(a.q_row_begin + r) * a.d;
+    const float *qsrc = a.queries + (size_t)ql * a.d;
     for (int i = lane; i < a.d; i += 32) qrow[i] = qsrc[i];
     __syncwarp();
 
     // error bound of the tensor-core score for this row (see the certificate below)
     double eps = 0.0;
     const double sigma = (double)scale_from_maxabs_bits(a.sc->maxabs_bits);
-    const double xn2 = a.qnorm64[a.q_row_begin + r];
+    const double xn2 = a.qnorm64[ql];
     {
         const double ymax = (double)__uint_as_float(a.sc->ymax_bits);
         const double xn = sqrt(xn2) * sigma * (1.0 + 1e-12);
@@ -782,7 +492,8 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         // debug: the bound must dominate the real error of every score the kernel produced
         float worst = 0.0f;
         for (int i = lane; i < n; i += 32) {
-            const uint32_t id = key_pos(keys[i]);
+            const uint32_t pos = key_pos(keys[i]);
+            const uint32_t id = a.base_perm ? (uint32_t)a.base_perm[pos] : pos;
             const float s_tc = -key_score(keys[i]);
             const float *brow = a.base + (size_t)id * a.d;
             double dot = 0.0;
@@ -794,12 +505,14 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         }
         for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
         if (lane == 0)
-            atomicMax(const_cast<uint32_t *>(&a.sc->pad[0]), __float_as_uint(worst));
+            atomicMax(const_cast<uint32_t *>(&a.sc->eps_ratio_bits), __float_as_uint(worst));
     }
 
-    // exact distances: the scalar sequence of get_real_dist, one candidate per lane
+    // exact distances: the scalar sequence of get_real_dist, one candidate per lane; keys are
+    // rebuilt on (distance, base row) so that ties order by the caller's row numbers
     for (int i = lane; i < n; i += 32) {
-        const uint32_t id = key_pos(keys[i]);
+        const uint32_t pos = key_pos(keys[i]);
+        const uint32_t id = a.base_perm ? (uint32_t)a.base_perm[pos] : pos;
         const float *brow = a.base + (size_t)id * a.d;
         float acc = 0.0f;
         if ((a.d & 3) == 0) {
@@ -848,6 +561,10 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
             const double dk = (double)key_score(keys[a.kcap - 1]);
             ok = lb > dk;
         }
+    } else if (n < a.kcap && n < a.nb - (a.self_join ? 1 : 0)) {
+        // no threshold and fewer candidates than the base could give: scores the filter could
+        // not compare (NaN / Inf input); the exact kernel decides
+        ok = false;
     }
 
     const size_t orow = (size_t)(q - a.out_q_begin) * a.k;
@@ -957,11 +674,10 @@ int pick_L(int kcap, bool inexact) {
     if (!inexact) {
         // exact operands: the certificate only has to absorb the accumulation bound, a
         // margin of half the neighbours is plenty; a short list keeps the threshold tight
-        const char *e = getenv("PQH_TC_LEXACT");
-        if (e) return atoi(e);
+        if (env().l_exact > 0) return env().l_exact;
         return (kcap + kcap / 2 + 7) / 8 * 8;
     }
-    if (const char *e = getenv("PQH_TC_LINEXACT")) return atoi(e);
+    if (env().l_inexact > 0) return env().l_inexact;
     // rounded operands: 64 candidates, or twice the neighbours asked for if that is more.
     // Measured (profiles/README.md): GIST-shaped k=16 needs 64 (at 32, 10 % of the rows fail the
     // certificate); Deep-shaped k=32 certifies every row at 64 and runs 1.5x faster than at 128.
@@ -972,132 +688,124 @@ int pick_L(int kcap, bool inexact) {
 }
 // list capacity: the filter checks it once per tile, after up to TC_BN (128) appends
 int pick_gcap(int L) {
-    static const char *e = getenv("PQH_TC_GCAP");  // experiments: 256 or 512
-    if (e && (atoi(e) == 256 || atoi(e) == 512) && L <= 96) return atoi(e);
+    const int e = env().gcap;
+    if ((e == 256 || e == 512) && L <= 96) return e;
     return L <= 96 ? 256 : 512;
 }
 
-template <int GCAP>
-size_t tc2_smem_bytes(const TcPlan &p) {
-    return 1024 + (size_t)p.a_bytes / 2 + (size_t)TC2_NSTAGE * p.b_bytes +
-           sizeof(Tc2SmemTail<GCAP>);
+size_t tc_smem_bytes(const TcPlan &p, int nepi) {
+    return 1024 + (size_t)p.a_bytes + (size_t)TC_NSTAGE * p.b_bytes + sizeof(TcSmemTail) +
+           (nepi == 16 ? (size_t)TC_ROWS * 2 * sizeof(uint64_t) : 0);
 }
-template <int GCAP>
-size_t tc_smem_bytes(const TcPlan &p) {
-    return 1024 + (size_t)p.a_bytes + (size_t)TC_NSTAGE * p.b_bytes + sizeof(TcSmemTail<GCAP>);
-}
-
-struct TcLayout {
-    size_t xh_b, xh_q, fold_b, fold_a, norm_b, norm_q, scalars, cand, cnt, tau, fb_rows, total;
-    size_t a8;  // integer path: u8 query operand [n_rows x d32] (0 when the path is disabled)
-    int d32;
-    // second pass (rows that failed the first certificate, redone with longer lists)
-    size_t p2_q, p2_xh, p2_norm, p2_cand, p2_cnt, p2_tau, p2_fb;
-    int p2_rows;  // rows per second-pass batch
-    int d16, L, L_exact, gcap, nsplit, n_qtiles, n_btiles, tiles_per_split;
-    int variant, halves, nlists;
-    int q_tail0, ns_tail, tiles_per_split_tail, qrows;  // tail of the work list (TcArgs)
-    size_t n_slots;                                      // candidate lists in all
-};
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Kernel variants.  1 = single-CTA kernel with the query tile resident in shared memory
-// (knn_tc_kernel; default whenever the tile fits, d <= ~144); 4 = streaming kernel for larger d
-// (knn_tcs.cu).  PQH_TC_VARIANT=2 / 3 select the CTA-pair experiments (this file / knn_tc3.cu),
-// kept for A/B measurements -- see profiles/README.md for why they are not the default.
-int tc_variant() {
-    const char *v = getenv("PQH_TC_VARIANT");
-    const int x = v ? atoi(v) : 1;
-    return (x >= 1 && x <= 5) ? x : 1;
-}
-
-// does the resident-A plan of `variant` fit in shared memory for this d16 / list capacity?
-bool resident_fits(int variant, int d16, int gcap) {
+// does the resident-A plan fit in shared memory for this operand width?
+bool resident_fits(int op_cols, int nepi) {
     TcPlan p;
-    if (!build_plan(d16, &p)) return false;
-    if (variant == 3) return tc3_pick_nstage(&p) >= 2;
-    if (variant == 5) return tc5_pick_nstage(&p, d16) >= 3;
-    size_t smem;
-    if (variant == 2)
-        smem = gcap == 128 ? tc2_smem_bytes<128>(p)
-                           : (gcap == 256 ? tc2_smem_bytes<256>(p) : tc2_smem_bytes<512>(p));
-    else
-        smem = gcap == 128 ? tc_smem_bytes<128>(p)
-                           : (gcap == 256 ? tc_smem_bytes<256>(p) : tc_smem_bytes<512>(p));
-    return smem <= 227 * 1024;
-}
-
-int tc_pick_variant(int d16, int gcap) {
-    int v = tc_variant();
-    if (v != 4 && !resident_fits(v, d16, gcap)) v = 4;
-    return v;
+    if (!build_plan(op_cols, &p)) return false;
+    return tc_smem_bytes(p, nepi) <= 227 * 1024;
 }
 
 constexpr int P2_GCAP = 512, P2_MAX_LISTS = 4;
 
-// Integer path for data made of integers in [0, 255] (knn_tc_i8.cuh): taken whenever the data
-// qualifies; $PQH_TC_I8=0 keeps such data on the FP16 path (A/B measurements, tests of the FP16
-// error bound).  Read on every call so that one process can compare both.
-bool i8_enabled() {
-    const char *e = getenv("PQH_TC_I8");
-    return e ? atoi(e) != 0 : true;
-}
+// work decomposition of one launch: n_rows query rows against n_btiles base tiles
+struct TcGeom {
+    int n_qtiles, nsplit, tiles_per_split;
+    int q_tail0, ns_tail, tiles_per_split_tail;
+    size_t n_slots;  // (row, split) pairs; each holds npar lists
+};
 
-void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join, int num_sms,
-               TcLayout *lo, int L_override = 0) {
-    const int kcap = self_join ? k - 1 : k;
-    lo->d16 = (d + 15) / 16 * 16;
-    lo->L = L_override ? L_override : pick_L(kcap, true);
-    lo->L_exact = L_override ? L_override : pick_L(kcap, false);
-    lo->gcap = L_override ? P2_GCAP : pick_gcap(lo->L);
-    lo->variant = tc_pick_variant(lo->d16, lo->gcap);
-    lo->halves = 1;
-    const int bn = lo->variant == 2 ? 256 : (lo->variant == 5 ? tc5_tile_rows() : TC_BN);
-    const int units = lo->variant == 1 ? num_sms : num_sms / 2;
-    const int qrows = lo->variant == 3 ? 512 : TC_ROWS;  // query rows per work item
-    lo->n_qtiles = (n_rows + qrows - 1) / qrows;
-    lo->n_btiles = (nb + bn - 1) / bn;
+void tc_geom(int n_rows, int n_btiles, int gcap, int npar, int num_sms, TcGeom *g) {
+    g->n_qtiles = (n_rows + TC_ROWS - 1) / TC_ROWS;
     // Base splits: a work item is (query tile, base split).  A split costs a second candidate list
     // per row with its own warm-up (measured: 100k x 128 takes 5.0 / 6.7 / 8.6 ms with 1 / 2 / 4
     // splits although 4 splits fill the last round of the grid best), so the base is only split
     // when the query tiles alone cannot occupy every SM once.
-    const int max_lists = 2048 / lo->gcap;
+    const int max_lists = 2048 / (gcap * npar);
     int nsplit = 1;
-    while (lo->n_qtiles * nsplit < units && nsplit * 2 * lo->halves <= max_lists && nsplit < 4 &&
-           lo->n_btiles / (nsplit * 2) >= 16)
+    while (g->n_qtiles * nsplit < num_sms && nsplit * 2 <= max_lists && nsplit < 4 &&
+           n_btiles / (nsplit * 2) >= 16)
         nsplit *= 2;
-    if (const char *e = getenv("PQH_TC_NSPLIT")) {
-        const int v = atoi(e);
-        if (v >= 1 && v * lo->halves <= max_lists && lo->n_btiles / v >= 8) nsplit = v;
-    }
-    lo->nsplit = nsplit;
-    lo->nlists = nsplit * lo->halves;
-    lo->tiles_per_split = (lo->n_btiles + nsplit - 1) / nsplit;
+    if (env().nsplit >= 1 && env().nsplit <= max_lists && n_btiles / env().nsplit >= 8)
+        nsplit = env().nsplit;
+    g->nsplit = nsplit;
+    g->tiles_per_split = (n_btiles + nsplit - 1) / nsplit;
     // The last round of the persistent grid: if the query tiles left over after the full rounds
     // occupy at most half of the SMs, cut each of them into 2..4 base splits so the round
     // finishes in a fraction of an item time (8 GPUs x 125k rows: 489 tiles = 3 rounds + 45).
-    lo->qrows = qrows;
-    lo->q_tail0 = lo->n_qtiles;
-    lo->ns_tail = 1;
-    lo->tiles_per_split_tail = lo->n_btiles;
-    if ((lo->variant == 1 || lo->variant == 4) && nsplit == 1 && lo->n_qtiles > units &&
-        !getenv("PQH_TC_NO_TAIL")) {
-        const int rem = lo->n_qtiles % units;
-        int ns = rem > 0 ? units / rem : 1;
+    g->q_tail0 = g->n_qtiles;
+    g->ns_tail = 1;
+    g->tiles_per_split_tail = n_btiles;
+    if (nsplit == 1 && g->n_qtiles > num_sms && !env().no_tail) {
+        const int rem = g->n_qtiles % num_sms;
+        int ns = rem > 0 ? num_sms / rem : 1;
         if (ns > 4) ns = 4;
-        while (ns > 1 && (ns > max_lists || lo->n_btiles / ns < 16)) --ns;
+        while (ns > 1 && (ns > max_lists || n_btiles / ns < 16)) --ns;
         if (ns > 1) {
-            lo->q_tail0 = lo->n_qtiles - rem;
-            lo->ns_tail = ns;
-            lo->tiles_per_split_tail = (lo->n_btiles + ns - 1) / ns;
+            g->q_tail0 = g->n_qtiles - rem;
+            g->ns_tail = ns;
+            g->tiles_per_split_tail = (n_btiles + ns - 1) / ns;
         }
     }
+    const long long tail_row0 = (long long)g->q_tail0 * TC_ROWS;
+    const long long rows_main = tail_row0 < n_rows ? tail_row0 : n_rows;
+    g->n_slots = (size_t)rows_main * nsplit + (size_t)(n_rows - rows_main) * g->ns_tail;
+}
+
+// Device scratch of one search.  Everything that scales with the candidate lists is sized for
+// ONE ROW SLICE: the first pass runs slice by slice over the query rows, so the lists never
+// exceed $PQH_TC_SLICE_MB (2 GiB by default; a slice is a whole number of rounds of the
+// persistent grid), whatever n is.
+struct TcLayout {
+    int d16, d32, L, L_exact, gcap, npar, nepi, nmma, n_btiles;
+    bool streaming, order;
+    int slice_rows, slice_qtiles;
+    size_t scalars, xh_b, fold_b, fold_a, norm_b, norm_q, xq, cand, cnt, tau, fb_rows, order_ws;
+    // second pass (rows that failed the first certificate, redone with longer lists)
+    size_t p2_q, p2_xh, p2_norm, p2_cand, p2_cnt, p2_tau, p2_fb, p2_self;
+    int p2_rows;  // rows per second-pass batch
+    size_t total;
+};
+
+void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcLayout *lo) {
+    const TcEnv &ev = env();
+    const int kcap = self_join ? k - 1 : k;
+    lo->d16 = (d + 15) / 16 * 16;
+    lo->d32 = (d + 31) / 32 * 32;
+    lo->L = pick_L(kcap, true);
+    lo->L_exact = pick_L(kcap, false);
+    lo->gcap = pick_gcap(lo->L);
+    lo->nepi = ev.nepi;
+    lo->streaming = ev.streaming || !resident_fits(lo->d16, lo->nepi);
+    lo->nmma = lo->streaming ? 1 : ev.nmma;
+    lo->npar = lo->nepi / 8;
+    lo->order = ev.order && nb >= 8192;
+    lo->n_btiles = (nb + TC_BN - 1) / TC_BN;
+    // row slice: as many whole rounds of the grid as the list budget allows
     {
-        const long long tail_row0 = (long long)lo->q_tail0 * qrows;
-        const long long rows_main = tail_row0 < n_rows ? tail_row0 : n_rows;
-        lo->n_slots = (size_t)rows_main * lo->nlists + (size_t)(n_rows - rows_main) * lo->ns_tail;
+        const size_t per_row = (size_t)lo->gcap * lo->npar * sizeof(key64_t);
+        long long rows = (long long)((size_t)ev.slice_mb * 1024 * 1024 / per_row);
+        const long long round = (long long)num_sms * TC_ROWS;
+        rows = rows / round * round;
+        if (rows < round) rows = round;
+        if (rows > n_rows) rows = n_rows;
+        lo->slice_rows = (int)rows;
+        lo->slice_qtiles = (lo->slice_rows + TC_ROWS - 1) / TC_ROWS;
     }
+    // list slots of the largest slice (base splits only happen for small slices)
+    size_t max_slots = 0;
+    {
+        TcGeom g;
+        tc_geom(lo->slice_rows, lo->n_btiles, lo->gcap, lo->npar, num_sms, &g);
+        max_slots = g.n_slots;
+        const int last = n_rows % lo->slice_rows;
+        if (last) {
+            tc_geom(last, lo->n_btiles, lo->gcap, lo->npar, num_sms, &g);
+            if (g.n_slots > max_slots) max_slots = g.n_slots;
+        }
+    }
+    const size_t n_lists = max_slots * lo->npar;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -1106,20 +814,20 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
     };
     lo->scalars = take(sizeof(PrepScalars));
     lo->xh_b = take((size_t)nb * lo->d16 * sizeof(__half));
-    lo->xh_q = self_join ? lo->xh_b : take((size_t)nq_src_rows * lo->d16 * sizeof(__half));
     lo->fold_b = take((size_t)nb * FOLD_COLS * sizeof(__half));
     lo->fold_a = take((size_t)TC_ROWS * FOLD_COLS * sizeof(__half));
     lo->norm_b = take((size_t)nb * sizeof(double));
-    lo->norm_q = self_join ? lo->norm_b : take((size_t)nq_src_rows * sizeof(double));
-    lo->cand = take(lo->n_slots * lo->gcap * sizeof(key64_t));
-    lo->cnt = take(lo->n_slots * sizeof(int));
-    lo->tau = take(lo->n_slots * sizeof(float));
+    lo->norm_q = self_join ? lo->norm_b : take((size_t)n_rows * sizeof(double));
+    lo->xq = take((size_t)lo->slice_rows * lo->d16 * sizeof(__half));
+    lo->cand = take(n_lists * lo->gcap * sizeof(key64_t));
+    lo->cnt = take(n_lists * sizeof(int));
+    lo->tau = take(n_lists * sizeof(float));
     lo->fb_rows = take((size_t)n_rows * sizeof(int));
-    lo->d32 = (d + 31) / 32 * 32;
-    lo->a8 = i8_enabled() ? take((size_t)n_rows * lo->d32) : 0;
+    lo->order_ws = lo->order ? take(order_workspace_bytes(lo->slice_rows, nb, lo->slice_qtiles)) : 0;
     {
         int p2 = n_rows / 16;
         if (p2 < 2048) p2 = 2048;
+        if (p2 > 65536) p2 = 65536;
         if (p2 > n_rows) p2 = n_rows;
         lo->p2_rows = p2;
         lo->p2_q = take((size_t)p2 * d * sizeof(float));
@@ -1128,24 +836,66 @@ void tc_layout(int n_rows, int nq_src_rows, int nb, int d, int k, int self_join,
         lo->p2_cand = take((size_t)p2 * P2_MAX_LISTS * P2_GCAP * sizeof(key64_t));
         lo->p2_cnt = take((size_t)p2 * P2_MAX_LISTS * sizeof(int));
         lo->p2_tau = take((size_t)p2 * P2_MAX_LISTS * sizeof(float));
+        lo->p2_self = take((size_t)p2 * sizeof(int));
         lo->p2_fb = take((size_t)n_rows * sizeof(int));
     }
     lo->total = off + 1024;
 }
 
+template <int GCAP, bool I8, int NEPI, int NMMA>
+cudaError_t launch_tc_one(const TcMaps &maps, const TcArgs &args, size_t smem, int grid,
+                          cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<GCAP, I8, NEPI, NMMA>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    knn_tc_kernel<GCAP, I8, NEPI, NMMA>
+        <<<grid, tc_threads(NEPI) + (NMMA - 1) * 32, smem, stream>>>(maps, args);
+    return cudaGetLastError();
+}
+template <int GCAP, bool I8>
+cudaError_t launch_tc_cfg(const TcMaps &maps, const TcArgs &args, size_t smem, int grid, int nepi,
+                          int nmma, cudaStream_t stream) {
+    if (nepi == 16)
+        return nmma == 2 ? launch_tc_one<GCAP, I8, 16, 2>(maps, args, smem, grid, stream)
+                         : launch_tc_one<GCAP, I8, 16, 1>(maps, args, smem, grid, stream);
+    return nmma == 2 ? launch_tc_one<GCAP, I8, 8, 2>(maps, args, smem, grid, stream)
+                     : launch_tc_one<GCAP, I8, 8, 1>(maps, args, smem, grid, stream);
+}
+
 }  // namespace
+
+void tc_reload_env() {
+    TcEnv e;
+    e.i8 = env_int("PQH_TC_I8", 1) != 0;
+    e.order = env_int("PQH_TC_ORDER", 1) != 0;
+    e.nepi = env_int("PQH_TC_EPI", 8) == 16 ? 16 : 8;
+    e.nmma = env_int("PQH_TC_MMA", 1) == 2 ? 2 : 1;
+    e.l_exact = env_int("PQH_TC_LEXACT", 0);
+    e.l_inexact = env_int("PQH_TC_LINEXACT", 0);
+    e.gcap = env_int("PQH_TC_GCAP", 0);
+    e.nsplit = env_int("PQH_TC_NSPLIT", 0);
+    e.no_tail = env_int("PQH_TC_NO_TAIL", 0);
+    e.no_pass2 = env_int("PQH_TC_NO_PASS2", 0);
+    e.check_eps = env_int("PQH_TC_CHECK_EPS", 0);
+    e.debug = env_int("PQH_TC_DEBUG", 0);
+    e.streaming = env_int("PQH_TC_STREAM", 0) != 0;
+    e.slice_mb = env_int("PQH_TC_SLICE_MB", 2048);
+    if (e.slice_mb < 64) e.slice_mb = 64;
+    e.loaded = true;
+    g_env = e;
+}
 
 bool tc_supported(int n_rows, int nb, int d, int k, int self_join) {
     const int kcap = self_join ? k - 1 : k;
     if (kcap < 1 || kcap > 64) return false;  // list capacity 512 holds L = 128 candidates
     if (nb < 2048 || n_rows < 1) return false;
     if (d < 1 || d > 4096) return false;
-    return true;  // the streaming kernel takes every d the resident kernels cannot
+    return true;  // the streaming kernel takes every d the resident kernel cannot
 }
 
 size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_sms) {
     TcLayout lo;
-    tc_layout(n_rows, n_rows, nb, d, k, self_join, num_sms, &lo);
+    tc_layout(n_rows, nb, d, k, self_join, num_sms, &lo);
     return lo.total;
 }
 
@@ -1153,98 +903,125 @@ size_t tc_workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int n
 //   d_queries: self-join -> same matrix as d_base (row q is query q);
 //              otherwise a matrix whose row (q - q_row0) is query q.
 // Rows that fail the certificate are written to *h_fb_count / d_fb_rows (absolute ids);
-// the caller redoes them with the exact kernel.  Synchronises the stream once.
+// the caller redoes them with the exact kernel.  Synchronises the stream: once to learn which
+// operand flavour the data allows, once for the number of rows that failed (and once more after
+// a second pass).
 cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row0, int q_begin,
                           int out_q_begin, int n_rows, int nb, int d, int k, int self_join,
                           int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
                           int num_sms, cudaStream_t stream, int *launches, int **d_fb_rows_out,
-                          unsigned *h_fb_count, cudaEvent_t *ev, TcTimes *times) {
+                          unsigned *h_fb_count, TcTimes *times) {
     *h_fb_count = 0;
     if (n_rows <= 0) return cudaSuccess;
+    const TcEnv &ev = env();
     const int kcap = self_join ? k - 1 : k;
     TcLayout lo;
-    tc_layout(n_rows, n_rows, nb, d, k, self_join, num_sms, &lo);
+    tc_layout(n_rows, nb, d, k, self_join, num_sms, &lo);
     if (lo.total > work_bytes) return cudaErrorMemoryAllocation;
     unsigned char *w = reinterpret_cast<unsigned char *>(
         ((uintptr_t)d_work + 1023) & ~(uintptr_t)1023);
     PrepScalars *sc = reinterpret_cast<PrepScalars *>(w + lo.scalars);
     __half *xh_b = reinterpret_cast<__half *>(w + lo.xh_b);
-    __half *xh_q = reinterpret_cast<__half *>(w + lo.xh_q);
     __half *fold_b = reinterpret_cast<__half *>(w + lo.fold_b);
     __half *fold_a = reinterpret_cast<__half *>(w + lo.fold_a);
     double *norm_b = reinterpret_cast<double *>(w + lo.norm_b);
     double *norm_q = reinterpret_cast<double *>(w + lo.norm_q);
+    void *xq = w + lo.xq;
     key64_t *cand = reinterpret_cast<key64_t *>(w + lo.cand);
     int *cnt = reinterpret_cast<int *>(w + lo.cnt);
     float *tau = reinterpret_cast<float *>(w + lo.tau);
     int *fb_rows = reinterpret_cast<int *>(w + lo.fb_rows);
+    void *order_ws = w + lo.order_ws;
     *d_fb_rows_out = fb_rows;
+    const int debug_mode = ev.debug;
+
+    // events: [0],[1] bracket the preparation; per slice (gemm start, gemm end, re-rank end)
+    const int n_slices = (n_rows + lo.slice_rows - 1) / lo.slice_rows;
+    std::vector<cudaEvent_t> evs;
+    if (times) {
+        evs.resize(2 + 3 * (size_t)n_slices);
+        for (auto &x : evs) cudaEventCreate(&x);
+    }
+    struct EvGuard {
+        std::vector<cudaEvent_t> &v;
+        ~EvGuard() {
+            for (auto x : v) cudaEventDestroy(x);
+        }
+    } ev_guard{evs};
 
     cudaError_t e;
-    if (ev) cudaEventRecord(ev[0], stream);
+    if (times) cudaEventRecord(evs[0], stream);
     if ((e = cudaMemsetAsync(sc, 0, sizeof(PrepScalars), stream)) != cudaSuccess) return e;
 
-    // queries of this launch: rows [q_src0, q_src0 + n_rows) of d_queries
+    // queries of this call: row (q - q_begin + q_src0) of q_mat
+    const float *q_mat = self_join ? d_base : d_queries;
     const int q_src0 = self_join ? q_begin : q_begin - q_row0;
-    const char *dbg_env = getenv("PQH_TC_DEBUG");
-    const int debug_mode = dbg_env ? atoi(dbg_env) : 0;
 
-    // ---- prep, integer flavour (opt-in): tried first, kept only if every value qualifies ----
+    // ---- locality order of the base (once per search) ----
+    OrderOut oo = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (lo.order) {
+        if ((e = launch_order_base(d_base, nb, d, lo.slice_rows, lo.slice_qtiles, order_ws, stream,
+                                   launches, &oo)) != cudaSuccess)
+            return e;
+    }
+    const int *base_perm = oo.base_perm;
+
+    // ---- base operand, integer flavour: tried first, kept only if every value qualifies ----
     bool used_i8 = false;
-    uint8_t *a8 = reinterpret_cast<uint8_t *>(w + lo.a8);
-    if (i8_enabled() && lo.variant == 1 && debug_mode == 0 &&
-        resident_fits(1, lo.d32 / 2, lo.gcap)) {
-        const float *qsrc = (self_join ? d_base : d_queries) + (size_t)q_src0 * d;
+    const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode == 0 || debug_mode == 1) &&
+                             resident_fits(lo.d32 / 2, lo.nepi);
+    if (i8_possible) {
         prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(
             d_base, nb, d, lo.d32, reinterpret_cast<uint8_t *>(xh_b), norm_b,
-            reinterpret_cast<int8_t *>(fold_b), 1, sc);
-        prep_rows_i8_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(
-            qsrc, n_rows, d, lo.d32, a8, self_join ? nullptr : norm_q, nullptr, 0, sc);
+            reinterpret_cast<int8_t *>(fold_b), 1, base_perm, 0, sc);
+        ++*launches;
+        if (!self_join) {  // the queries must qualify too: check them all, build nothing yet
+            prep_rows_i8_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(
+                q_mat + (size_t)q_src0 * d, n_rows, d, lo.d32, nullptr, nullptr, nullptr, 0,
+                nullptr, 0, sc);
+            ++*launches;
+        }
         fold_const_i8_kernel<<<(TC_ROWS * 32 + 255) / 256, 256, 0, stream>>>(
             reinterpret_cast<uint8_t *>(fold_a));
-        *launches += 3;
+        ++*launches;
         PrepScalars probe;
         if ((e = cudaMemcpyAsync(&probe, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost,
                                  stream)) != cudaSuccess)
             return e;
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-        used_i8 = probe.pad[2] == 0;
+        used_i8 = probe.i8_reject == 0;
     }
 
-    // ---- prep, FP16 flavour ----
-    auto prep_fp16 = [&]() {
+    // ---- base operand, FP16 flavour ----
+    auto prep_base_fp16 = [&]() {
         const int grid_ma = num_sms * 8;
         maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_base, (size_t)nb * d, &sc->maxabs_bits);
         ++*launches;
         if (!self_join) {
-            maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
+            maxabs_kernel<<<grid_ma, 256, 0, stream>>>(q_mat + (size_t)q_src0 * d,
                                                        (size_t)n_rows * d, &sc->maxabs_bits);
             ++*launches;
         }
         prep_rows_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d16, xh_b, norm_b,
-                                                           fold_b, 1, sc);
-        ++*launches;
-        if (!self_join) {
-            prep_rows_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(d_queries + (size_t)q_src0 * d,
-                                                                   n_rows, d, lo.d16, xh_q, norm_q,
-                                                                   nullptr, 0, sc);
-            ++*launches;
-        }
+                                                           fold_b, 1, base_perm, 0, sc);
         fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
-        ++*launches;
+        *launches += 2;
     };
-    if (!used_i8) prep_fp16();
+    if (!used_i8) prep_base_fp16();
+    if (times) cudaEventRecord(evs[1], stream);
 
     // ---- one pass = tensor-core kernel + re-rank over a set of query rows ----
     struct Pass {
-        const TcLayout *lo;      // geometry (tiles, splits, list sizes) of this pass
-        const __half *xh_q;      // FP16 operand whose row (q_op_begin + r) is query r
+        TcGeom g;
+        int L_exact, L_inexact, gcap, npar, nepi, nmma;
+        bool streaming;
+        const void *a_op;        // query operand: row (q_op_begin + r) is query row r
         uint64_t a_rows;         // rows of that operand
         int q_op_begin;
-        const float *q_mat;      // FP32 matrix whose row (q_row_begin + r) is query r
-        int q_row_begin;
-        const double *qnorm64;   // indexed like q_mat
-        const int *row_ids;      // absolute query ids (second pass) or null
+        const float *queries;    // FP32 rows of the pass's queries (see RerankArgs)
+        const double *qnorm64;   // indexed like `queries`
+        int q_begin;             // absolute query id of row 0 (natural order) / of queries[0]
+        const int *row_ids, *q_perm, *q_self, *qt_start;
         int n_rows;
         key64_t *cand;
         int *cnt;
@@ -1252,114 +1029,83 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         int *fb_rows;
         uint32_t *fb_count;
         bool i8;                 // integer operands (first pass only)
-        const void *b_op;        // base operand rows
         int op_cols;             // operand row length in 2-byte units (the tensor maps' view)
+        cudaEvent_t *ev3;        // gemm start / gemm end / re-rank end, or null
     };
     auto run_pass = [&](const Pass &p) -> cudaError_t {
-        const TcLayout &pl = *p.lo;
         TcMaps maps;
         TcArgs args;
-        if (!build_plan(p.op_cols, &args.plan) && pl.variant != 4) return cudaErrorInvalidValue;
+        if (!build_plan(p.op_cols, &args.plan) && !p.streaming) return cudaErrorInvalidValue;
         const uint32_t boxc[3] = {64, 32, 16};
-        const uint32_t a_box_rows = pl.variant == 2 ? 128 : TC_ROWS;
-        const uint32_t b_box_rows =
-            pl.variant == 3 ? 64 : (pl.variant == 5 ? tc5_tile_rows() : TC_BN);
         for (int c = 0; c < 3; ++c) {
             // classes a small d never uses still need a legal box
             const uint32_t bc = boxc[c] <= (uint32_t)p.op_cols ? boxc[c] : 16;
-            if (!make_map(&maps.a[c], p.xh_q, p.a_rows, p.op_cols, bc, a_box_rows) ||
-                !make_map(&maps.b[c], p.b_op, nb, p.op_cols, bc, b_box_rows))
+            if (!make_map(&maps.a[c], p.a_op, p.a_rows, p.op_cols, bc, TC_ROWS) ||
+                !make_map(&maps.b[c], xh_b, nb, p.op_cols, bc, TC_BN))
                 return cudaErrorInvalidValue;
         }
-        if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, a_box_rows) ||
-            !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, b_box_rows))
+        if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, TC_ROWS) ||
+            !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, TC_BN))
             return cudaErrorInvalidValue;
 
         args.n_rows = p.n_rows;
-        args.q_begin = q_begin;
+        args.q_begin = p.q_begin;
         args.q_op_begin = p.q_op_begin;
         args.nb = nb;
         args.self_join = self_join;
         args.row_ids = p.row_ids;
-        args.n_qtiles = pl.n_qtiles;
-        args.nsplit = pl.nsplit;
-        args.q_tail0 = pl.q_tail0;
-        args.ns_tail = pl.ns_tail;
-        args.tiles_per_split_tail = pl.tiles_per_split_tail;
-        args.tiles_per_split = pl.tiles_per_split;
-        args.n_btiles = pl.n_btiles;
+        args.q_self = p.q_self;
+        args.qt_start = p.qt_start;
+        args.n_qtiles = p.g.n_qtiles;
+        args.nsplit = p.g.nsplit;
+        args.q_tail0 = p.g.q_tail0;
+        args.ns_tail = p.g.ns_tail;
+        args.tiles_per_split_tail = p.g.tiles_per_split_tail;
+        args.tiles_per_split = p.g.tiles_per_split;
+        args.n_btiles = lo.n_btiles;
         args.debug_mode = debug_mode;
-        args.nstage = 0;
         args.kcap = kcap;
-        args.L_exact = pl.L_exact;
-        args.L_inexact = pl.L;
+        args.L_exact = p.L_exact;
+        args.L_inexact = p.L_inexact;
         args.sc = sc;
         args.cand = p.cand;
         args.cand_cnt = p.cnt;
         args.cand_tau = p.tau;
 
-        const int n_items = pl.q_tail0 * pl.nsplit + (pl.n_qtiles - pl.q_tail0) * pl.ns_tail;
-        size_t smem;
+        const int n_items =
+            p.g.q_tail0 * p.g.nsplit + (p.g.n_qtiles - p.g.q_tail0) * p.g.ns_tail;
         cudaError_t pe;
-#define LAUNCH_TC(KERNEL, SMEM, GRID)                                                            \
-    do {                                                                                         \
-        smem = (SMEM);                                                                           \
-        if ((pe = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                       (int)smem)) != cudaSuccess)                               \
-            return pe;                                                                           \
-        KERNEL<<<(GRID), TC_THREADS, smem, stream>>>(maps, args);                                \
-    } while (0)
-        if (pl.variant == 5) {
-            args.nstage = tc5_pick_nstage(&args.plan, pl.d16);
-            if (args.nstage < 3) return cudaErrorInvalidValue;
-            if ((pe = launch_tc5(&maps, &args, p.xh_q, fold_a, pl.gcap, pl.d16, n_items, num_sms,
-                                 stream)) != cudaSuccess)
-                return pe;
-        } else if (pl.variant == 4) {
-            if ((pe = launch_tcs(&maps, &args, pl.gcap, pl.d16, n_items, num_sms, stream)) !=
+        if (p.ev3) cudaEventRecord(p.ev3[0], stream);
+        if (p.streaming) {
+            if ((pe = launch_tcs(&maps, &args, p.gcap, lo.d16, n_items, num_sms, p.nepi, stream)) !=
                 cudaSuccess)
                 return pe;
-        } else if (pl.variant == 3) {
-            args.nstage = tc3_pick_nstage(&args.plan);
-            if (args.nstage < 2) return cudaErrorInvalidValue;
-            if ((pe = launch_tc3(&maps, &args, pl.gcap, n_items, num_sms, stream)) != cudaSuccess)
-                return pe;
-        } else if (pl.variant == 2) {
-            const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
-            const int grid = 2 * clusters;
-            if (pl.gcap == 256) LAUNCH_TC(knn_tc2_kernel<256>, tc2_smem_bytes<256>(args.plan), grid);
-            else LAUNCH_TC(knn_tc2_kernel<512>, tc2_smem_bytes<512>(args.plan), grid);
         } else {
             const int grid = n_items < num_sms ? n_items : num_sms;
-            // the PROF instantiations carry the clock64()/counter instrumentation (PQH_TC_DEBUG)
-            if (debug_mode != 0) {
-                if (pl.gcap == 256)
-                    LAUNCH_TC((knn_tc_kernel<256, true, false>), tc_smem_bytes<256>(args.plan), grid);
-                else
-                    LAUNCH_TC((knn_tc_kernel<512, true, false>), tc_smem_bytes<512>(args.plan), grid);
-            } else if (p.i8) {
-                if (pl.gcap == 256)
-                    LAUNCH_TC((knn_tc_kernel<256, false, true>), tc_smem_bytes<256>(args.plan), grid);
-                else
-                    LAUNCH_TC((knn_tc_kernel<512, false, true>), tc_smem_bytes<512>(args.plan), grid);
-            } else if (pl.gcap == 256) {
-                LAUNCH_TC((knn_tc_kernel<256, false, false>), tc_smem_bytes<256>(args.plan), grid);
-            } else {
-                LAUNCH_TC((knn_tc_kernel<512, false, false>), tc_smem_bytes<512>(args.plan), grid);
-            }
+            const size_t smem = tc_smem_bytes(args.plan, p.nepi);
+            if (p.i8)
+                pe = p.gcap == 256 ? launch_tc_cfg<256, true>(maps, args, smem, grid, p.nepi,
+                                                               p.nmma, stream)
+                                   : launch_tc_cfg<512, true>(maps, args, smem, grid, p.nepi,
+                                                               p.nmma, stream);
+            else
+                pe = p.gcap == 256 ? launch_tc_cfg<256, false>(maps, args, smem, grid, p.nepi,
+                                                                p.nmma, stream)
+                                   : launch_tc_cfg<512, false>(maps, args, smem, grid, p.nepi,
+                                                                p.nmma, stream);
+            if (pe != cudaSuccess) return pe;
         }
-#undef LAUNCH_TC
         ++*launches;
-        if ((pe = cudaGetLastError()) != cudaSuccess) return pe;
-        if (ev && !p.row_ids) cudaEventRecord(ev[2], stream);
+        if (p.ev3) cudaEventRecord(p.ev3[1], stream);
 
         // ---- re-rank + certificate ----
         RerankArgs ra;
         ra.base = d_base;
-        ra.queries = p.q_mat;
-        ra.q_row_begin = p.q_row_begin;
-        ra.q_begin = q_begin;
+        ra.queries = p.queries;
+        ra.q_begin = p.q_begin;
         ra.row_ids = p.row_ids;
+        ra.q_perm = p.q_perm;
+        ra.base_perm = base_perm;
         ra.out_q_begin = out_q_begin;
         ra.n_rows = p.n_rows;
         ra.nb = nb;
@@ -1367,24 +1113,26 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         ra.k = k;
         ra.kcap = kcap;
         ra.self_join = self_join;
-        ra.nlists = pl.nlists;
-        ra.tail_row0 = pl.q_tail0 * pl.qrows;
-        ra.ns_tail = pl.ns_tail;
-        ra.gcap = pl.gcap;
+        ra.nlists = p.g.nsplit;
+        ra.npar = p.npar;
+        ra.tail_row0 = p.g.q_tail0 * TC_ROWS;
+        ra.ns_tail = p.g.ns_tail;
+        ra.gcap = p.gcap;
         ra.cand = p.cand;
         ra.cand_cnt = p.cnt;
         ra.cand_tau = p.tau;
         ra.qnorm64 = p.qnorm64;
         ra.bnorm64 = norm_b;
-        ra.check_eps = getenv("PQH_TC_CHECK_EPS") ? 1 : 0;
+        ra.check_eps = ev.check_eps;
         ra.sc = sc;
-        ra.ksteps = (pl.d16 + FOLD_COLS) / 16;
+        ra.ksteps = (lo.d16 + FOLD_COLS) / 16;
         ra.i8 = p.i8 ? 1 : 0;
         ra.assign = d_assign;
         ra.dis = d_dis;
         ra.fb_rows = p.fb_rows;
         ra.fb_count = p.fb_count;
-        const int nmax = pl.gcap * (pl.nlists > pl.ns_tail ? pl.nlists : pl.ns_tail);
+        const int splits = p.g.nsplit > p.g.ns_tail ? p.g.nsplit : p.g.ns_tail;
+        const int nmax = p.gcap * splits * p.npar;
         const int rgrid = (p.n_rows + RR_WARPS - 1) / RR_WARPS;
         const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
 #define LAUNCH_RR(N)                                                                             \
@@ -1402,47 +1150,97 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         else LAUNCH_RR(2048);
 #undef LAUNCH_RR
         ++*launches;
+        if (p.ev3) cudaEventRecord(p.ev3[2], stream);
         return cudaGetLastError();
     };
 
-    // ---- first pass: every row of this launch ----
-    if (ev) cudaEventRecord(ev[1], stream);
-    Pass p1;
-    p1.lo = &lo;
-    p1.i8 = used_i8;
-    p1.b_op = xh_b;
-    p1.op_cols = used_i8 ? lo.d32 / 2 : lo.d16;
-    p1.xh_q = used_i8 ? reinterpret_cast<const __half *>(a8) : xh_q;
-    p1.a_rows = (self_join && !used_i8) ? (uint64_t)nb : (uint64_t)n_rows;
-    p1.q_op_begin = (self_join && !used_i8) ? q_begin : 0;
-    p1.q_mat = self_join ? d_base : d_queries;
-    p1.q_row_begin = q_src0;
-    p1.qnorm64 = self_join ? norm_b : norm_q - q_src0;  // indexed by q_row_begin + r
-    p1.row_ids = nullptr;
-    p1.n_rows = n_rows;
-    p1.cand = cand;
-    p1.cnt = cnt;
-    p1.tau = tau;
-    p1.fb_rows = fb_rows;
-    p1.fb_count = &sc->fb_count;
-    if ((e = run_pass(p1)) != cudaSuccess) return e;
+    // ---- first pass: the rows of this call, slice by slice ----
+    for (int si = 0; si < n_slices; ++si) {
+        const int s_begin = q_begin + si * lo.slice_rows;  // absolute id of the slice's row 0
+        const int rows = (n_rows - si * lo.slice_rows) < lo.slice_rows
+                             ? (n_rows - si * lo.slice_rows)
+                             : lo.slice_rows;
+        const float *q_slice = q_mat + (size_t)(q_src0 + si * lo.slice_rows) * d;
+        double *qn_slice = (self_join ? norm_b + s_begin : norm_q + (size_t)si * lo.slice_rows);
+        Pass p1;
+        tc_geom(rows, lo.n_btiles, lo.gcap, lo.npar, num_sms, &p1.g);
+        if (lo.order) {
+            if ((e = launch_order_queries(self_join ? nullptr : q_slice, s_begin, rows, nb, d,
+                                          self_join, p1.g.n_qtiles, lo.slice_rows,
+                                          lo.slice_qtiles, order_ws, stream, launches, &oo)) !=
+                cudaSuccess)
+                return e;
+        }
+        // query operand of the slice
+        if (used_i8) {
+            prep_rows_i8_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(
+                q_slice, rows, d, lo.d32, static_cast<uint8_t *>(xq), self_join ? nullptr : qn_slice,
+                nullptr, 0, oo.q_perm, s_begin, sc);
+            ++*launches;
+            p1.a_op = xq;
+            p1.a_rows = (uint64_t)rows;
+            p1.q_op_begin = 0;
+        } else if (self_join && !lo.order) {
+            p1.a_op = xh_b;  // query q is operand row q of the base
+            p1.a_rows = (uint64_t)nb;
+            p1.q_op_begin = s_begin;
+        } else {
+            prep_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(
+                q_slice, rows, d, lo.d16, static_cast<__half *>(xq),
+                self_join ? nullptr : qn_slice, nullptr, 0, oo.q_perm, s_begin, sc);
+            ++*launches;
+            p1.a_op = xq;
+            p1.a_rows = (uint64_t)rows;
+            p1.q_op_begin = 0;
+        }
+        p1.L_exact = lo.L_exact;
+        p1.L_inexact = lo.L;
+        p1.gcap = lo.gcap;
+        p1.npar = lo.npar;
+        p1.nepi = lo.nepi;
+        p1.nmma = lo.nmma;
+        p1.streaming = lo.streaming;
+        p1.i8 = used_i8;
+        p1.op_cols = used_i8 ? lo.d32 / 2 : lo.d16;
+        p1.queries = q_slice;
+        p1.qnorm64 = qn_slice;
+        p1.q_begin = s_begin;
+        p1.row_ids = nullptr;
+        p1.q_perm = oo.q_perm;
+        p1.q_self = oo.q_self;
+        p1.qt_start = oo.qt_start;
+        p1.n_rows = rows;
+        p1.cand = cand;
+        p1.cnt = cnt;
+        p1.tau = tau;
+        p1.fb_rows = fb_rows;
+        p1.fb_count = &sc->fb_count;
+        p1.ev3 = times ? &evs[2 + 3 * (size_t)si] : nullptr;
+        if ((e = run_pass(p1)) != cudaSuccess) return e;
+    }
 
-    if (ev) cudaEventRecord(ev[3], stream);
     PrepScalars hsc;
     if ((e = cudaMemcpyAsync(&hsc, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost, stream)) !=
         cudaSuccess)
         return e;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
     *h_fb_count = hsc.fb_count;
+    if (times && hsc.fb_count > 0) {
+        const size_t keep = hsc.fb_count < (1u << 20) ? hsc.fb_count : (1u << 20);
+        times->pass1_failed.resize(keep);
+        if ((e = cudaMemcpyAsync(times->pass1_failed.data(), fb_rows, keep * sizeof(int),
+                                 cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+            return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    }
 
     // ---- second pass: rows whose certificate failed, redone with four times longer lists.
     //      Their cost on the exact kernel would be ~1000x a tensor-core row, so a data set on
     //      which a few per cent of the rows fail must not fall off a cliff.  Skipped when most
     //      rows fail (FP16 cannot resolve this data at all) or when there are only a handful.
     const unsigned n_fb1 = hsc.fb_count;
-    if (n_fb1 >= 64 && n_fb1 <= (unsigned)n_rows / 2 && !getenv("PQH_TC_NO_PASS2") &&
-        debug_mode == 0) {
-        const int L1 = hsc.inexact ? lo.L : lo.L_exact;
+    if (n_fb1 >= 64 && n_fb1 <= (unsigned)n_rows / 2 && !ev.no_pass2 && debug_mode == 0) {
+        const int L1 = (hsc.inexact && !used_i8) ? lo.L : lo.L_exact;
         int L2 = 4 * L1;
         if (L2 > 192) L2 = 192;
         if (L2 > L1) {
@@ -1450,55 +1248,69 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                 if ((e = cudaMemsetAsync(&sc->maxabs_bits, 0, 3 * sizeof(uint32_t), stream)) !=
                     cudaSuccess)
                     return e;
-                prep_fp16();
+                prep_base_fp16();
             }
             float *q2 = reinterpret_cast<float *>(w + lo.p2_q);
             __half *xh2 = reinterpret_cast<__half *>(w + lo.p2_xh);
             double *norm2 = reinterpret_cast<double *>(w + lo.p2_norm);
             int *fb2 = reinterpret_cast<int *>(w + lo.p2_fb);
-            uint32_t *fb2_count = &sc->pad[1];
+            int *self2 = reinterpret_cast<int *>(w + lo.p2_self);
             const float *src = self_join ? d_base : d_queries;
             const int src_row0 = self_join ? 0 : q_row0;
+            const bool stream2 = ev.streaming || !resident_fits(lo.d16, 8);
             for (unsigned done = 0; done < n_fb1; done += (unsigned)lo.p2_rows) {
                 const int n2 = (int)(n_fb1 - done < (unsigned)lo.p2_rows ? n_fb1 - done
                                                                           : (unsigned)lo.p2_rows);
                 const int *ids = fb_rows + done;
-                TcLayout lo2;
-                tc_layout(n2, n2, nb, d, k, self_join, num_sms, &lo2, L2);
-                if (lo2.nlists > P2_MAX_LISTS || lo2.ns_tail > P2_MAX_LISTS)
+                Pass p2;
+                tc_geom(n2, lo.n_btiles, P2_GCAP, 1, num_sms, &p2.g);
+                if (p2.g.nsplit > P2_MAX_LISTS || p2.g.ns_tail > P2_MAX_LISTS)
                     return cudaErrorInvalidValue;
                 gather_rows_kernel<<<(n2 + 7) / 8, 256, 0, stream>>>(src, src_row0, ids, n2, d, q2);
                 prep_rows_kernel<<<(n2 + 7) / 8, 256, 0, stream>>>(q2, n2, d, lo.d16, xh2, norm2,
-                                                                   nullptr, 0, sc);
+                                                                   nullptr, 0, nullptr, 0, sc);
                 *launches += 2;
+                p2.q_self = nullptr;
+                if (lo.order && self_join) {
+                    if ((e = launch_order_self_of(ids, n2, oo.base_inv, self2, stream, launches)) !=
+                        cudaSuccess)
+                        return e;
+                    p2.q_self = self2;
+                }
                 if ((e = cudaMemsetAsync(&sc->tile_cursor, 0, sizeof(uint32_t), stream)) !=
                     cudaSuccess)
                     return e;
-                Pass p2;
-                p2.lo = &lo2;
-                p2.xh_q = xh2;
+                p2.L_exact = p2.L_inexact = L2;
+                p2.gcap = P2_GCAP;
+                p2.npar = 1;
+                p2.nepi = 8;
+                p2.nmma = 1;
+                p2.streaming = stream2;
+                p2.a_op = xh2;
                 p2.a_rows = (uint64_t)n2;
                 p2.q_op_begin = 0;
-                p2.q_mat = q2;
-                p2.q_row_begin = 0;
+                p2.queries = q2;
                 p2.qnorm64 = norm2;
+                p2.q_begin = q_begin;
                 p2.row_ids = ids;
+                p2.q_perm = nullptr;
+                p2.qt_start = nullptr;
                 p2.n_rows = n2;
                 p2.cand = reinterpret_cast<key64_t *>(w + lo.p2_cand);
                 p2.cnt = reinterpret_cast<int *>(w + lo.p2_cnt);
                 p2.tau = reinterpret_cast<float *>(w + lo.p2_tau);
                 p2.fb_rows = fb2;
-                p2.fb_count = fb2_count;
+                p2.fb_count = &sc->fb2_count;
                 p2.i8 = false;
-                p2.b_op = xh_b;
                 p2.op_cols = lo.d16;
+                p2.ev3 = nullptr;
                 if ((e = run_pass(p2)) != cudaSuccess) return e;
             }
             if ((e = cudaMemcpyAsync(&hsc, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost,
                                      stream)) != cudaSuccess)
                 return e;
             if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-            *h_fb_count = hsc.pad[1];
+            *h_fb_count = hsc.fb2_count;
             *d_fb_rows_out = fb2;
             if (times) times->rows_pass2 = (long long)n_fb1;
         }
@@ -1508,29 +1320,26 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         times->candidates = 0;
         for (int i = 0; i < 32; ++i) times->candidates += (double)hsc.cand_total[i];
         times->inexact = used_i8 ? 2 : (int)hsc.inexact;
+        times->slices = n_slices;
         {
             union { uint32_t u; float f; } cv;
-            cv.u = hsc.pad[0];
+            cv.u = hsc.eps_ratio_bits;
             times->eps_ratio_max = cv.f;
         }
-        if (dbg_env) {
+        if (debug_mode)
             fprintf(stderr,
-                    "tc dbg: slow_tiles=%llu hard_shrinks=%llu idle_shrinks=%llu chunks=%llu | "
-                    "epi warps: wait %.3g work %.3g cyc | mma thread: wait_b %.3g wait_acc %.3g "
-                    "total %.3g cyc (sums over CTAs) | pass-1 failures %u\n",
-                    hsc.dbg[0], hsc.dbg[1], hsc.dbg[2], hsc.dbg[3], (double)hsc.dbg[4],
-                    (double)hsc.dbg[5], (double)hsc.dbg[6], (double)hsc.dbg[7],
-                    (double)hsc.cand_total[63], n_fb1);
-            fprintf(stderr,
-                    "tc dbg: filter_tile cycles: load+maxima %.3g release(no hit) %.3g slow %.3g "
-                    "hard-shrink %.3g\n",
-                    (double)hsc.cand_total[40], (double)hsc.cand_total[41],
-                    (double)hsc.cand_total[42], (double)hsc.cand_total[43]);
-        }
-        if (ev) {
-            cudaEventElapsedTime(&times->ms_prep, ev[0], ev[1]);
-            cudaEventElapsedTime(&times->ms_gemm, ev[1], ev[2]);
-            cudaEventElapsedTime(&times->ms_rerank, ev[2], ev[3]);
+                    "tc dbg: mma threads: barrier waits %.4g cyc of %.4g cyc (sums over CTAs and "
+                    "issuers) | pass-1 failures %u | epi %d mma %d order %d slices %d\n",
+                    (double)hsc.dbg[0], (double)hsc.dbg[1], n_fb1, lo.nepi, lo.nmma,
+                    (int)lo.order, n_slices);
+        cudaEventElapsedTime(&times->ms_prep, evs[0], evs[1]);
+        times->ms_gemm = times->ms_rerank = 0.f;
+        for (int si = 0; si < n_slices; ++si) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, evs[2 + 3 * (size_t)si], evs[3 + 3 * (size_t)si]);
+            cudaEventElapsedTime(&b, evs[3 + 3 * (size_t)si], evs[4 + 3 * (size_t)si]);
+            times->ms_gemm += a;
+            times->ms_rerank += b;
         }
     }
     return cudaSuccess;

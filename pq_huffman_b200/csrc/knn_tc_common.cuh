@@ -1,4 +1,13 @@
-// knn_tc_common.cuh -- definitions shared by the tensor-core kernels (knn_tc.cu, knn_tc3.cu).
+// knn_tc_common.cuh -- definitions shared by the tensor-core kernels (knn_tc.cu: query tile
+// resident in shared memory; knn_tcs.cu: both operands streamed): work decomposition, the
+// candidate-list bookkeeping and the whole filter epilogue.
+//
+// Scores.  FP16 operands give an FP32 score S' (larger = nearer); the integer flavour for data
+// made of integers in [0, 255] (tcgen05.mma kind::i8, u8 x s8 -> s32) gives the EXACT score
+//     T = x.(y - 128) - ceil(|y|^2 / 2),   dist = |x|^2 - 256 sum(x) - 2 T - (0 or 1),
+// so the only slack its certificate needs is that 0/1.  Score<I8> hides the difference; the
+// candidate keys (high word: order-reversing map of the score, low word: base position) have the
+// same layout in both, so shrink_row and the re-rank kernel are shared.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -13,9 +22,17 @@ constexpr int TC_ROWS = 256;    // query rows per CTA: two M=128 accumulator til
 constexpr int TC_BN = 128;      // base rows per tile (UMMA N)
 constexpr int TC_NSTAGE = 4;    // B-tile ring
 constexpr int TC_MAXSEG = 6;
-constexpr int TC_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int TC_EPI_WARPS = 8;
 constexpr int FOLD_COLS = 16;
+// warp 0 TMA, warp 1 MMA, then NEPI filter warps: 8 (each warp filters every tile of its 32 rows)
+// or 16 (two warps per 32 rows, one per accumulator stage; see epilogue_warps)
+__host__ __device__ constexpr int tc_threads(int nepi) { return (2 + nepi) * 32; }
+// registers per thread of a one-CTA-per-SM kernel: the 64K file over the warps, in units of 8
+__host__ __device__ constexpr int tc_max_regs(int threads) {
+    return 65536 / threads / 8 * 8 > 255 ? 255 : 65536 / threads / 8 * 8;
+}
+
+constexpr int I8_FOLD_FULL = 30;         // fold columns with A-side constant 255 (the last two: 1)
+constexpr int I8_FOLD_UNIT = 255 * 128;  // what one full column can subtract
 
 struct TcSeg {
     int k_off;   // element offset in the fp16 operand row (data segments)
@@ -37,10 +54,13 @@ struct PrepScalars {
     uint32_t ymax_bits;    // max scaled base norm |y'| (float bits, rounded up)
     uint32_t inexact;      // some fp16(sigma*x) != sigma*x
     uint32_t fb_count;     // rows that failed the certificate
-    uint32_t tile_cursor;  // base tile most recently started by some CTA (L2-friendly order)
-    uint32_t pad[3];
-    unsigned long long cand_total[64];
-    unsigned long long dbg[8];  // epilogue event counters: slow chunks, appends, hard/idle shrinks, chunks  // candidates re-ranked (spread to avoid contention)
+    uint32_t tile_cursor;  // base tile most recently started by CTA 0 (L2-friendly order)
+    uint32_t eps_ratio_bits;  // PQH_TC_CHECK_EPS: max |S'_tensor - S'_fp64| / eps (float bits)
+    uint32_t fb2_count;    // rows that failed the certificate of the second pass
+    uint32_t i8_reject;    // integer path: bit 0 = a value is not an integer in [0, 255],
+                           // bit 1 = |y|^2 beyond the capacity of the fold columns
+    unsigned long long cand_total[32];  // candidates re-ranked (spread to avoid contention)
+    unsigned long long dbg[8];          // PQH_TC_DEBUG: MMA-thread cycle counters
 };
 
 struct TcArgs {
@@ -50,13 +70,18 @@ struct TcArgs {
     int nb;
     int self_join;
     const int *row_ids;  // second pass: absolute query id of each row (null: q_begin + row)
+    // Locality order (knn_order.cu): operand row p of the base is data row base_perm[p], query
+    // row r of this launch is data row q_perm[r].  q_self[r] = position of query r's own vector
+    // in the base operand (self-join; -1 otherwise) and qt_start[qt] = base tile at which query
+    // tile qt starts its sweep (the cell its rows belong to).  All null: natural order.
+    const int *q_self;
+    const int *qt_start;
     int n_qtiles, nsplit, tiles_per_split, n_btiles;
     // Tail of the work list: the last n_qtiles - q_tail0 query tiles (the partly filled last
     // round of the persistent grid) are cut into ns_tail base splits each so that every SM gets
     // a piece; their rows own ns_tail candidate lists instead of nsplit.
     int q_tail0, ns_tail, tiles_per_split_tail;
     int kcap;        // neighbours needed per row (k, or k-1 for a self-join)
-    int nstage;      // pair kernel: depth of the B-tile ring
     int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
     int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
     const PrepScalars *sc;
@@ -98,7 +123,7 @@ __device__ __forceinline__ ItemInfo decode_item(const TcArgs &a, int item) {
     if (it.t_hi > a.n_btiles) it.t_hi = a.n_btiles;
     return it;
 }
-// candidate-list slot of (query row r of this launch, base split sp)
+// candidate-list slot of (query row r of this launch, base split sp); a slot holds `npar` lists
 __host__ __device__ __forceinline__ size_t list_slot(int r, int sp, int tail_row0, int nsplit,
                                                       int ns_tail) {
     return r < tail_row0 ? (size_t)r * nsplit + sp
@@ -106,25 +131,32 @@ __host__ __device__ __forceinline__ size_t list_slot(int r, int sp, int tail_row
 }
 
 // Base-tile order of one work item.  Every CTA sweeps ALL tiles of its range, so the order is
-// free: CTA 0 never restarts -- it keeps cycling through the tiles and publishes its position --
-// and every other CTA starts a new item at CTA 0's current tile and wraps around.  All CTAs then
-// stream the same window of the base operand at any moment, and a tile is fetched from HBM once
-// per sweep of the pack instead of once per CTA.  (Single writer: a cursor written by every CTA
-// never converges.)
-__device__ __forceinline__ int item_start_tile(const PrepScalars *sc, int t_lo, int t_hi,
+// free.
+//  * Locality order (qt_start given): the sweep starts at the cell the query tile's own rows
+//    belong to, so a row meets its near neighbours in the first few tiles and its threshold is
+//    tight for the rest of the sweep.  CTAs work on neighbouring query tiles at any moment, so
+//    they still stream one window of the base together.
+//  * Natural order: CTA 0 never restarts -- it keeps cycling through the tiles and publishes
+//    its position -- and every other CTA starts a new item at CTA 0's current tile and wraps
+//    around.  All CTAs then stream the same window of the base operand at any moment, and a
+//    tile is fetched from HBM once per sweep of the pack instead of once per CTA.  (Single
+//    writer: a cursor written by every CTA never converges.)
+__device__ __forceinline__ int item_start_tile(const TcArgs &a, int qt, int t_lo, int t_hi,
                                                int my_next) {
     int c = my_next;
-    if (blockIdx.x != 0)
-        c = (int)*reinterpret_cast<const volatile uint32_t *>(&sc->tile_cursor);
+    if (a.qt_start)
+        c = a.qt_start[qt];
+    else if (blockIdx.x != 0)
+        c = (int)*reinterpret_cast<const volatile uint32_t *>(&a.sc->tile_cursor);
     return (c >= t_lo && c < t_hi) ? c : t_lo;
 }
 __device__ __forceinline__ int item_tile(int i, int t0, int t_lo, int t_hi) {
     int t = t0 + i;
     return t >= t_hi ? t - (t_hi - t_lo) : t;
 }
-__device__ __forceinline__ void publish_cursor(const PrepScalars *sc, int t) {
-    if (blockIdx.x == 0)
-        *reinterpret_cast<volatile uint32_t *>(&const_cast<PrepScalars *>(sc)->tile_cursor) =
+__device__ __forceinline__ void publish_cursor(const TcArgs &a, int t) {
+    if (blockIdx.x == 0 && !a.qt_start)
+        *reinterpret_cast<volatile uint32_t *>(&const_cast<PrepScalars *>(a.sc)->tile_cursor) =
             (uint32_t)t;
 }
 
@@ -147,6 +179,47 @@ __host__ __device__ __forceinline__ float scale_from_maxabs_bits(uint32_t bits) 
     union { uint32_t u; float f; } c; c.u = sb; return c.f;
 #endif
 }
+
+// ------------------------------------------------------------------------------------
+// score flavours
+template <bool I8>
+struct Score;
+template <>
+struct Score<false> {  // FP32 accumulator of FP16 operands
+    typedef float T;
+    static __device__ __forceinline__ T lowest() { return __int_as_float(0xff800000); }
+    static __device__ __forceinline__ T highest() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ T from_bits(uint32_t b) { return __uint_as_float(b); }
+    static __device__ __forceinline__ T max2(T a, T b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ T max3(T a, T b, T c) { return ptx::fmax3(a, b, c); }
+    // float_to_ordered(-score) straight from the accumulator bits: hi = bits ^ (~sign & 0x7fffffff)
+    static __device__ __forceinline__ uint32_t hi(uint32_t bits) {
+        uint32_t sign, h;
+        asm("shr.s32 %0, %1, 31;" : "=r"(sign) : "r"(bits));
+        asm("lop3.b32 %0, %1, %2, 0x7fffffff, 0xD2;" : "=r"(h) : "r"(bits), "r"(sign));
+        return h;
+    }
+    static __device__ __forceinline__ T from_hi(uint32_t h) { return -ordered_to_float(h); }
+    static __device__ __forceinline__ float as_float(T t) { return t; }
+};
+template <>
+struct Score<true> {  // s32 accumulator of u8 x s8 operands
+    typedef int T;
+    static __device__ __forceinline__ T lowest() { return (int)0x80000000; }
+    static __device__ __forceinline__ T highest() { return 0x7fffffff; }
+    static __device__ __forceinline__ T from_bits(uint32_t b) { return (int)b; }
+    static __device__ __forceinline__ T max2(T a, T b) { return max(a, b); }
+    static __device__ __forceinline__ T max3(T a, T b, T c) { return max(max(a, b), c); }
+    static __device__ __forceinline__ uint32_t hi(uint32_t bits) { return bits ^ 0x7fffffffu; }
+    static __device__ __forceinline__ T from_hi(uint32_t h) { return (int)(h ^ 0x7fffffffu); }
+    // |score| < 2^24: exact as a float; "no threshold yet" = -inf
+    static __device__ __forceinline__ float as_float(T t) {
+        return t == lowest() ? __int_as_float(0xff800000) : (float)t;
+    }
+};
+// the same order-reversing maps on the host / in the re-rank kernel
+__host__ __device__ __forceinline__ uint32_t i32_score_to_hi(int s) { return (uint32_t)s ^ 0x7fffffffu; }
+__host__ __device__ __forceinline__ int i32_hi_to_score(uint32_t h) { return (int)(h ^ 0x7fffffffu); }
 
 // Warp-cooperative shrink of one row's candidate list (n <= NMAX keys in global memory) to its
 // best L .. L+L/2 keys.  A bisection on the ordered score bits, bracketed by the list's own
@@ -225,15 +298,40 @@ __device__ __noinline__ uint32_t shrink_row(key64_t *list, int n, int L, int lan
     return x;
 }
 
-// Predicated append of (ordered(-score), id) to a row's candidate list: no branch.
+// Shrink the lists of the lanes flagged in `need` (warp-uniform), one after the other; the lane
+// that owns a list takes its new length and raises its threshold to the pivot's score.
+template <int GCAP, bool I8, bool SIZED>
+__device__ __forceinline__ void shrink_flagged(unsigned need, int L, int lane,
+                                               typename Score<I8>::T &tau, int &cnt,
+                                               key64_t *list) {
+    typedef Score<I8> S;
+#pragma unroll 1
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        key64_t *l = reinterpret_cast<key64_t *>(
+            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
+        const int n = __shfl_sync(0xffffffffu, cnt, src);
+        int kept;
+        uint32_t x;
+        if (SIZED)  // idle-time shrinks run early, on short lists: size the register copy to fit
+            x = n <= 64    ? shrink_row<64>(l, n, L, lane, kept)
+                : n <= 128 ? shrink_row<128>(l, n, L, lane, kept)
+                           : shrink_row<GCAP>(l, n, L, lane, kept);
+        else
+            x = shrink_row<GCAP>(l, n, L, lane, kept);
+        if (lane == src) {
+            cnt = kept;
+            tau = S::max2(tau, S::from_hi(x));
+        }
+    }
+}
+
+// Predicated append of (hi(score), id) to a row's candidate list: no branch.
+template <bool I8>
 __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint32_t score_bits,
                                           int id) {
-    // float_to_ordered(-score) straight from the bits of score: two instructions
-    // hi = bits ^ (~sign & 0x7fffffff)
-    uint32_t sign, hi;
-    asm("shr.s32 %0, %1, 31;" : "=r"(sign) : "r"(score_bits));
-    asm("lop3.b32 %0, %1, %2, 0x7fffffff, 0xD2;" : "=r"(hi) : "r"(score_bits), "r"(sign));
-    const key64_t key = ((key64_t)hi << 32) | (key64_t)(uint32_t)id;
+    const key64_t key = ((key64_t)Score<I8>::hi(score_bits) << 32) | (key64_t)(uint32_t)id;
     asm volatile(
         "{\n\t"
         ".reg .pred q;\n\t"
@@ -246,51 +344,79 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
     cnt += p ? 1 : 0;
 }
 
+// maxima of the two groups of 8 columns held in v[0..16)
+template <bool I8>
+__device__ __forceinline__ void group_maxima16(const uint32_t (&v)[16],
+                                               typename Score<I8>::T *gm) {
+    typedef Score<I8> S;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint32_t *b = &v[q * 8];
+        typename S::T m = S::max3(S::from_bits(b[0]), S::from_bits(b[1]), S::from_bits(b[2]));
+        m = S::max3(m, S::from_bits(b[3]), S::from_bits(b[4]));
+        m = S::max3(m, S::from_bits(b[5]), S::from_bits(b[6]));
+        gm[q] = S::max2(m, S::from_bits(b[7]));
+    }
+}
+
 // Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
 // it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
 //
 // Hot path (kept small and contiguous -- it must live in the instruction cache): copy the
-// 32 x 128 slice to registers with two 64-column tcgen05.ld in flight together, reduce it to
-// 16 group maxima (groups of 8 columns) with 3-input max, compare with the row's threshold tau
-// and OR the 16-bit result over the warp.  No bit set (the common case): release the
-// accumulator stage and return.
+// 32 x 128 slice to registers, reduce it to 16 group maxima (groups of 8 columns) with 3-input
+// max, compare with the row's threshold tau and OR the 16-bit result over the warp.  No bit set
+// (the common case): release the accumulator stage and return.  WIDE (8 filter warps, 168
+// registers): two 64-column tcgen05.ld in flight together; otherwise (16 filter warps: 20 warps
+// per CTA leave 96 registers per thread) eight 16-column loads, two in flight, the maxima of
+// one computed while the next is on its way.
 // Slow path (one small loop, no unrolled copies): for every flagged group re-read its 8 columns
 // from TMEM by address and append the scores above tau to the row's candidate list with
 // predicated stores (no divergent branches); then release the stage, then -- rarely -- shrink a
 // list that reached its hard capacity.
-// tau_shared (pair kernel): ordered bits of the threshold shared by the two threads that
-// filter the two column halves of the same row.
-template <int GCAP, int NCOLS, class Release>
-__device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool special, int ib_hi,
+template <int GCAP, bool I8, bool WIDE, class Release>
+__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
                                             int self, int L, int lane, int debug_mode,
-                                            uint32_t *tau_shared, float &tau, int &cnt,
-                                            key64_t *list, unsigned (&ctr)[4], Release release,
-                                            long long *tprof = nullptr) {
-    const long long tp0 = tprof ? clock64() : 0;
-    static_assert(NCOLS == 128 || NCOLS == 80, "tile widths: 64 + 64 or 64 + 16 columns");
-    constexpr int NG = NCOLS / 8;  // groups of 8 columns
+                                            typename Score<I8>::T &tau, int &cnt, key64_t *list,
+                                            Release release) {
+    typedef Score<I8> S;
+    typedef typename S::T T;
+    constexpr int NG = TC_BN / 8;  // groups of 8 columns
     unsigned groups = 0;
     {
-        uint32_t ra[64], rb[NCOLS - 64];
-        ptx::tmem_ld_32x32b_x64(tbase, ra);
-        if constexpr (NCOLS == 128) ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
-        else ptx::tmem_ld_32x32b_x16(tbase + 64, rb);
-        ptx::tmem_wait_ld();
-        // group maxima (groups of 8 columns), then the row maximum
-        float gm[NG];
+        T gm[NG];
+        if constexpr (WIDE) {
+            uint32_t ra[64], rb[64];
+            ptx::tmem_ld_32x32b_x64(tbase, ra);
+            ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+            ptx::tmem_wait_ld();
 #pragma unroll
-        for (int q = 0; q < NG; ++q) {
-            const uint32_t *buf = (q < 8) ? &ra[q * 8] : &rb[(q - 8) * 8];
-            float m = ptx::fmax3(__uint_as_float(buf[0]), __uint_as_float(buf[1]),
-                                 __uint_as_float(buf[2]));
-            m = ptx::fmax3(m, __uint_as_float(buf[3]), __uint_as_float(buf[4]));
-            m = ptx::fmax3(m, __uint_as_float(buf[5]), __uint_as_float(buf[6]));
-            gm[q] = fmaxf(m, __uint_as_float(buf[7]));
+            for (int q = 0; q < NG; ++q) {
+                const uint32_t *b = (q < 8) ? &ra[q * 8] : &rb[(q - 8) * 8];
+                T m = S::max3(S::from_bits(b[0]), S::from_bits(b[1]), S::from_bits(b[2]));
+                m = S::max3(m, S::from_bits(b[3]), S::from_bits(b[4]));
+                m = S::max3(m, S::from_bits(b[5]), S::from_bits(b[6]));
+                gm[q] = S::max2(m, S::from_bits(b[7]));
+            }
+        } else {
+            // two 16-column loads in flight; the wait is not selective (it completes every load
+            // issued so far), so each round waits for the older one and reissues its buffer
+            uint32_t r0[16], r1[16];
+            ptx::tmem_ld_32x32b_x16(tbase, r0);
+            ptx::tmem_ld_32x32b_x16(tbase + 16, r1);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                ptx::tmem_wait_ld_16(r0);
+                group_maxima16<I8>(r0, gm + 2 * c);
+                if (c + 2 < 8) ptx::tmem_ld_32x32b_x16(tbase + 16 * (c + 2), r0);
+                ptx::tmem_wait_ld_16(r1);
+                group_maxima16<I8>(r1, gm + 2 * c + 2);
+                if (c + 3 < 8) ptx::tmem_ld_32x32b_x16(tbase + 16 * (c + 3), r1);
+            }
         }
-        float rm = gm[0];
+        T rm = gm[0];
 #pragma unroll
-        for (int q = 1; q + 1 < NG; q += 2) rm = ptx::fmax3(rm, gm[q], gm[q + 1]);
-        if ((NG & 1) == 0) rm = fmaxf(rm, gm[NG - 1]);
+        for (int q = 1; q + 1 < NG; q += 2) rm = S::max3(rm, gm[q], gm[q + 1]);
+        rm = S::max2(rm, gm[NG - 1]);
         // common case: no row of the warp has anything above its threshold -> one vote, done
         if (__any_sync(0xffffffffu, rm > tau)) {
             unsigned gmask = 0;
@@ -299,16 +425,10 @@ __device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool
             groups = __reduce_or_sync(0xffffffffu, gmask);
         }
     }
-    const long long tp1 = tprof ? clock64() : 0;
     if (groups == 0 || debug_mode == 2) {
         release();
-        if (tprof) {
-            tprof[0] += tp1 - tp0;
-            tprof[1] += clock64() - tp1;
-        }
         return;
     }
-    ++ctr[0];
     const int id_lim = special ? ib_hi : 0x7fffffff;
     // the id checks (ragged last tile, the row's own column) are only compiled into the copy of
     // the scan that "special" tiles take; the choice is made warp-uniform
@@ -319,13 +439,13 @@ __device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int id = col0 + j;
-                const bool p = (__uint_as_float(v8[j]) > tau) & (id < id_lim) & (id != self);
-                append_if(p, list, cnt, v8[j], id);
+                const bool p = (S::from_bits(v8[j]) > tau) & (id < id_lim) & (id != self);
+                append_if<I8>(p, list, cnt, v8[j], id);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                append_if(__uint_as_float(v8[j]) > tau, list, cnt, v8[j], col0 + j);
+                append_if<I8>(S::from_bits(v8[j]) > tau, list, cnt, v8[j], col0 + j);
         }
     };
     const int q1 = __ffs(groups) - 1;
@@ -354,75 +474,154 @@ __device__ __forceinline__ void filter_tile_n(uint32_t tbase, int col_base, bool
         release();
     }
     if (cnt > GCAP) __trap();  // list overflow would silently corrupt a neighbouring row's list
-    const long long tp2 = tprof ? clock64() : 0;
-    // hard capacity: a tile can append up to NCOLS entries before this check runs again
-    unsigned need = __ballot_sync(0xffffffffu, cnt > GCAP - NCOLS);
-#pragma unroll 1
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        key64_t *l = reinterpret_cast<key64_t *>(
-            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-        const int n = __shfl_sync(0xffffffffu, cnt, src);
-        int kept;
-        const uint32_t x = shrink_row<GCAP>(l, n, L, lane, kept);
-        ++ctr[1];
-        if (lane == src) {
-            cnt = kept;
-            tau = fmaxf(tau, -ordered_to_float(x));
-            if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
-        }
-    }
-    if (tprof) {
-        tprof[0] += tp1 - tp0;          // TMEM -> registers, group maxima
-        tprof[2] += tp2 - tp1;          // slow path up to the release
-        tprof[3] += clock64() - tp2;    // hard shrinks
-    }
-}
-
-template <int GCAP, class Release>
-__device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
-                                            int self, int L, int lane, int debug_mode,
-                                            uint32_t *tau_shared, float &tau, int &cnt,
-                                            key64_t *list, unsigned (&ctr)[4], Release release,
-                                            long long *tprof = nullptr) {
-    filter_tile_n<GCAP, TC_BN>(tbase, col_base, special, ib_hi, self, L, lane, debug_mode,
-                               tau_shared, tau, cnt, list, ctr, release, tprof);
+    // hard capacity: a tile can append up to TC_BN entries before this check runs again
+    shrink_flagged<GCAP, I8, false>(__ballot_sync(0xffffffffu, cnt > GCAP - TC_BN), L, lane, tau,
+                                    cnt, list);
 }
 
 // While the tensor cores have not finished the next accumulator tile, use the idle time to
-// shrink lists that have grown past 2L: the threshold then stays fresh without a shrink ever
+// shrink lists that have grown past 1.5 L: the threshold then stays fresh without a shrink ever
 // standing between a finished accumulator stage and its release (mandatory shrinks at the hard
-// capacity GCAP-32 remain in filter_tile, but become rare).
-template <int GCAP>
+// capacity remain in filter_tile, but become rare).  The loop condition is made warp-uniform:
+// the body runs full-mask collectives.
+template <int GCAP, bool I8>
 __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
-                                                           int lane, uint32_t *tau_shared,
-                                                           float &tau, int &cnt, key64_t *list,
-                                                           unsigned (&ctr)[4]) {
+                                                           int lane, typename Score<I8>::T &tau,
+                                                           int &cnt, key64_t *list) {
     const int soft = (L + L / 2 < GCAP - TC_BN) ? L + L / 2 : GCAP - TC_BN;
-    while (!ptx::mbar_test_wait(bar, parity)) {
+    while (!__all_sync(0xffffffffu, ptx::mbar_test_wait(bar, parity))) {
         const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
         if (need == 0) {
             ptx::mbar_wait(bar, parity);
             return;
         }
-        const int src = __ffs(need) - 1;
-        key64_t *l = reinterpret_cast<key64_t *>(
-            __shfl_sync(0xffffffffu, (unsigned long long)list, src));
-        const int n = __shfl_sync(0xffffffffu, cnt, src);
-        int kept;
-        const uint32_t x = n <= 64    ? shrink_row<64>(l, n, L, lane, kept)
-                           : n <= 128 ? shrink_row<128>(l, n, L, lane, kept)
-                                      : shrink_row<GCAP>(l, n, L, lane, kept);
-        ++ctr[2];
-        if (lane == src) {
-            cnt = kept;
-            tau = fmaxf(tau, -ordered_to_float(x));
-            if (tau_shared) atomicMax(tau_shared, float_to_ordered(tau));
-        }
+        shrink_flagged<GCAP, I8, true>(need & (0u - need), L, lane, tau, cnt, list);
     }
 }
 
+// Thresholds exchanged between the two warps that share 32 query rows when there are 16 filter
+// warps: (work item << 32) | bits of tau, one 8-byte word per (row, warp of the pair).  A
+// threshold is a statement about the ROW ("at least L candidates of this row score >= tau"),
+// so either warp may adopt the other's; the item tag keeps a warp that is already in the next
+// work item from reading a threshold of the previous one.
+template <bool I8>
+__device__ __forceinline__ uint64_t pack_tau(int item, typename Score<I8>::T tau) {
+    uint32_t b;
+    if constexpr (I8) b = (uint32_t)tau;
+    else b = __float_as_uint(tau);
+    return ((uint64_t)(uint32_t)item << 32) | b;
+}
+
+// The filter warps of one CTA: filter warp e (0 .. NEPI-1) owns TMEM lane quadrant `quad` of
+// query tile g = (e >> 2) & 1, i.e. 32 query rows, one per lane.
+//   NEPI == 8:  the warp filters every base tile of the sweep for its rows.
+//   NEPI == 16: warps e and e + 8 share the same 32 rows; warp e takes the tiles that land in
+//               accumulator stage 0 (even steps), warp e + 8 those of stage 1.  Each keeps its
+//               own candidate list and count (list index 2 * slot + stage) and they exchange
+//               thresholds through shared memory (tau_x).  Twice the warps per scheduler hide
+//               the tensor-memory and barrier latencies of the hot path, and a warp has two tile
+//               times for a slow tile.
+// Steps are numbered over the whole life of the CTA (gstep): stage = step & 1, barrier phase =
+// (step >> 1) & 1.
+// Barriers and hand-over words the filter warps use, in the shared-memory tail of both kernels.
+struct EpiBars {
+    uint64_t acc_full[2], acc_empty[2];
+    uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
+    uint32_t tmem_base;
+    int item_t0[2];     // first base tile of the current / next work item (set by the producer)
+};
+
+template <int GCAP, bool I8, int NEPI>
+__device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int quad, int lane,
+                                               EpiBars *eb, uint64_t *tau_x) {
+    typedef Score<I8> S;
+    typedef typename S::T T;
+    constexpr int NPAR = NEPI / 8;
+    const int g = (e >> 2) & 1;
+    const int par = e >> 3;  // 0 when NEPI == 8
+    // quad = warp index & 3: the TMEM lane quadrant this warp may read; four consecutive warps
+    // cover the four quadrants whatever the index of the first filter warp is
+    const int row_in_cta = g * 128 + quad * 32 + lane;
+    const uint32_t tmem_row = eb->tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 128);
+    const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
+    const int n_items = total_items(args);
+    uint32_t gstep = 0;
+    int it_par = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemInfo it = decode_item(args, item);
+        const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
+        const int r = qt * TC_ROWS + row_in_cta;
+        const bool valid = r < args.n_rows;
+        int self = -1;
+        if (valid && args.self_join)
+            self = args.q_self ? args.q_self[r] : (args.row_ids ? args.row_ids[r] : args.q_begin + r);
+        const size_t slot =
+            valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail) * NPAR + par
+                  : 0;
+        key64_t *list = args.cand + slot * GCAP;
+        T tau = valid ? S::lowest() : S::highest();
+        T tau_pub = tau;
+        int cnt = 0;
+        long long b_hi = (long long)t_hi * TC_BN;
+        if (b_hi > args.nb) b_hi = args.nb;
+        const int ib_hi = (int)b_hi;
+        if (NPAR == 2) tau_x[row_in_cta * 2 + par] = pack_tau<I8>(item, tau);
+
+        const int nst = t_hi - t_lo;
+        int t0 = 0;
+        bool first = true;
+        for (int i = (NPAR == 2) ? (int)((par ^ gstep) & 1u) : 0; i < nst; i += NPAR) {
+            const uint32_t s = gstep + (uint32_t)i;
+            const int as = (int)(s & 1u);
+            const uint32_t acc_ph = (s >> 1) & 1u;
+            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
+            ptx::tc_fence_after_sync();
+            if (first) {
+                ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
+                t0 = *reinterpret_cast<volatile int *>(&eb->item_t0[it_par]);
+                first = false;
+            }
+            if (NPAR == 2) {
+                // adopt the partner's threshold if it belongs to this work item and is higher
+                const uint64_t px = *reinterpret_cast<volatile uint64_t *>(
+                    &tau_x[row_in_cta * 2 + (par ^ 1)]);
+                if ((int)(px >> 32) == item) {
+                    T pt;
+                    if constexpr (I8) pt = (int)(uint32_t)px;
+                    else pt = __uint_as_float((uint32_t)px);
+                    tau = S::max2(tau, pt);
+                }
+            }
+            const int t = item_tile(i, t0, t_lo, t_hi);
+            const uint32_t tbase = tmem_row + (uint32_t)(as * 256);
+            // id checks are only needed in the tile holding this row's own column and in
+            // the (possibly ragged) last tile
+            const int tile0 = t * TC_BN;
+            const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
+            auto release = [&]() {
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&eb->acc_empty[as]);
+            };
+            if (args.debug_mode != 1)
+                filter_tile<GCAP, I8, NEPI == 8>(tbase, tile0, special, ib_hi, self, L, lane,
+                                                 args.debug_mode, tau, cnt, list, release);
+            else
+                release();
+            if (NPAR == 2 && tau != tau_pub) {
+                *reinterpret_cast<volatile uint64_t *>(&tau_x[row_in_cta * 2 + par]) =
+                    pack_tau<I8>(item, tau);
+                tau_pub = tau;
+            }
+        }
+        gstep += (uint32_t)nst;
+        it_par ^= 1;
+        if (valid) {
+            args.cand_cnt[slot] = cnt;
+            args.cand_tau[slot] = S::as_float(tau);
+        }
+    }
+}
 
 }  // namespace
 }  // namespace pqh

@@ -2,7 +2,7 @@
 // does not fit in shared memory (GIST-shaped d = 960, anything above ~144).
 //
 // Same geometry and epilogue as knn_tc_kernel (256 query rows per CTA as two M=128 accumulator
-// tiles, base tiles of 128 rows, two accumulator stages, eight filter warps), but BOTH operands
+// tiles, base tiles of 128 rows, two accumulator stages, 8 or 16 filter warps), but BOTH operands
 // are streamed through one ring of K-blocks: a stage holds the [256 x 64] slice of the query
 // tile and the [128 x 64] slice of the base tile for one K-block (48 KB), the MMA thread
 // accumulates over all K-blocks of a tile before committing the accumulator.  With d this large
@@ -24,10 +24,7 @@ constexpr int TS_STAGE_BYTES = TS_A_BYTES + TS_B_BYTES;
 
 struct TsSmemTail {
     uint64_t full[TS_NSTAGE], empty[TS_NSTAGE];
-    uint64_t acc_full[2], acc_empty[2];
-    uint32_t tmem_base;
-    int item_t0[2];
-    uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
+    EpiBars eb;
 };
 
 // K-blocks of a padded operand row of d16 halves followed by the 16 fold columns:
@@ -73,13 +70,14 @@ struct KBlocks {
     }
 };
 
-template <int GCAP>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int GCAP, int NEPI>
+__global__ void __launch_bounds__(tc_threads(NEPI), 1) __maxnreg__(tc_max_regs(tc_threads(NEPI)))
 knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     TsSmemTail &tail = *reinterpret_cast<TsSmemTail *>(smem + TS_NSTAGE * TS_STAGE_BYTES);
+    uint64_t *tau_x = reinterpret_cast<uint64_t *>(&tail + 1);  // [256][2], NEPI == 16 only
     const KBlocks kb(d16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,17 +96,17 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
             ptx::mbar_init(&tail.empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&tail.acc_full[i], 1);
-            ptx::mbar_init(&tail.acc_empty[i], TC_EPI_WARPS);
+            ptx::mbar_init(&tail.eb.acc_full[i], 1);
+            ptx::mbar_init(&tail.eb.acc_empty[i], 8);
         }
-        ptx::mbar_init(&tail.t0_ready, 1);
+        ptx::mbar_init(&tail.eb.t0_ready, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<512>(&tail.tmem_base);
+    if (warp == 2) ptx::tmem_alloc<512>(&tail.eb.tmem_base);
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
-    const uint32_t tmem_base = tail.tmem_base;
+    const uint32_t tmem_base = tail.eb.tmem_base;
 
     const int n_items = total_items(args);
 
@@ -123,14 +121,14 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 const int arow = args.q_op_begin + qt * TC_ROWS;
                 // the slot of item i is reused by item i+2; the producer is at most one ring
                 // (a fraction of a tile) ahead of the MMA, the epilogue at most two tiles behind
-                const int t0 = item_start_tile(args.sc, t_lo, t_hi, my_next);
+                const int t0 = item_start_tile(args, qt, t_lo, t_hi, my_next);
                 my_next = t0;
-                tail.item_t0[it_par] = t0;
-                ptx::mbar_arrive(&tail.t0_ready);
+                tail.eb.item_t0[it_par] = t0;
+                ptx::mbar_arrive(&tail.eb.t0_ready);
                 it_par ^= 1;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {
                     const int t = item_tile(ti, t0, t_lo, t_hi);
-                    publish_cursor(args.sc, t);
+                    publish_cursor(args, t);
                     for (int i = 0; i < kb.total; ++i) {
                         int bytes, k_off, fold;
                         kb.get(i, bytes, k_off, fold);
@@ -164,7 +162,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 const ItemInfo it = decode_item(args, item);
                 const int t_lo = it.t_lo, t_hi = it.t_hi;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {
-                    ptx::mbar_wait(&tail.acc_empty[as], acc_ph ^ 1);
+                    ptx::mbar_wait(&tail.eb.acc_empty[as], acc_ph ^ 1);
                     ptx::tc_fence_after_sync();
                     for (int i = 0; i < kb.total; ++i) {
                         int bytes, k_off, fold;
@@ -191,7 +189,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                             ph ^= 1;
                         }
                     }
-                    ptx::umma_commit(&tail.acc_full[as]);
+                    ptx::umma_commit(&tail.eb.acc_full[as]);
                     as ^= 1;
                     if (as == 0) acc_ph ^= 1;
                 }
@@ -199,62 +197,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
         }
     } else {
         // ===================== epilogue: threshold filter (as knn_tc_kernel) =================
-        const int e = warp - 2;
-        const int g = e >> 2;
-        const int quad = warp & 3;
-        const int row_in_cta = g * 128 + quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
-        int as = 0;
-        uint32_t acc_ph = 0;
-        unsigned ctr[4] = {0, 0, 0, 0};
-        int it_par = 0;
-        const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const ItemInfo it = decode_item(args, item);
-            const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
-            const int r = qt * TC_ROWS + row_in_cta;
-            const bool valid = r < args.n_rows;
-            const int self = (valid && args.self_join)
-                                 ? (args.row_ids ? args.row_ids[r] : args.q_begin + r)
-                                 : -1;
-            const size_t slot = valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail)
-                                      : 0;
-            key64_t *list = args.cand + slot * GCAP;
-            float tau = valid ? NEG_INF : POS_INF;
-            int cnt = 0;
-            long long b_hi = (long long)t_hi * TC_BN;
-            if (b_hi > args.nb) b_hi = args.nb;
-            const int ib_hi = (int)b_hi;
-            int t0 = 0;
-            for (int ti = 0; ti < t_hi - t_lo; ++ti) {
-                wait_acc_with_idle_shrinks<GCAP>(&tail.acc_full[as], acc_ph, L, lane, nullptr, tau,
-                                                 cnt, list, ctr);
-                ptx::tc_fence_after_sync();
-                if (ti == 0) {
-                    ptx::mbar_wait(&tail.t0_ready, (uint32_t)it_par);
-                    t0 = *reinterpret_cast<volatile int *>(&tail.item_t0[it_par]);
-                }
-                const int t = item_tile(ti, t0, t_lo, t_hi);
-                const uint32_t tbase = tmem_base + lane_addr + (uint32_t)(as * 256 + g * 128);
-                const int tile0 = t * TC_BN;
-                const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
-                auto release = [&]() {
-                    ptx::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tail.acc_empty[as]);
-                };
-                filter_tile<GCAP>(tbase, tile0, special, ib_hi, self, L, lane, args.debug_mode,
-                                  nullptr, tau, cnt, list, ctr, release);
-                as ^= 1;
-                if (as == 0) acc_ph ^= 1;
-            }
-            it_par ^= 1;
-            if (valid) {
-                args.cand_cnt[slot] = cnt;
-                args.cand_tau[slot] = tau;
-            }
-        }
+        epilogue_warps<GCAP, false, NEPI>(args, warp - 2, warp & 3, lane, &tail.eb, tau_x);
     }
 
     ptx::tc_fence_before_sync();
@@ -262,28 +205,30 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+template <int GCAP, int NEPI>
+cudaError_t launch_tcs_one(const TcMaps &maps, const TcArgs &args, int d16, int grid,
+                           cudaStream_t stream) {
+    const size_t smem = 1024 + (size_t)TS_NSTAGE * TS_STAGE_BYTES + sizeof(TsSmemTail) +
+                        (NEPI == 16 ? (size_t)TC_ROWS * 2 * sizeof(uint64_t) : 0);
+    cudaError_t e = cudaFuncSetAttribute(knn_tcs_kernel<GCAP, NEPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    knn_tcs_kernel<GCAP, NEPI><<<grid, tc_threads(NEPI), smem, stream>>>(maps, args, d16);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_tcs(const void *maps_v, const void *args_v, int gcap, int d16, int n_items,
-                       int num_sms, cudaStream_t stream) {
+                       int num_sms, int nepi, cudaStream_t stream) {
     const TcMaps &maps = *static_cast<const TcMaps *>(maps_v);
     const TcArgs &args = *static_cast<const TcArgs *>(args_v);
     const int grid = n_items < num_sms ? n_items : num_sms;
-    const size_t smem = 1024 + (size_t)TS_NSTAGE * TS_STAGE_BYTES + sizeof(TsSmemTail);
-    cudaError_t e;
-#define LAUNCH_TS(G)                                                                             \
-    do {                                                                                         \
-        if ((e = cudaFuncSetAttribute(knn_tcs_kernel<G>,                                         \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != \
-            cudaSuccess)                                                                         \
-            return e;                                                                            \
-        knn_tcs_kernel<G><<<grid, TC_THREADS, smem, stream>>>(maps, args, d16);                  \
-    } while (0)
-    if (gcap == 128) LAUNCH_TS(128);
-    else if (gcap == 256) LAUNCH_TS(256);
-    else LAUNCH_TS(512);
-#undef LAUNCH_TS
-    return cudaGetLastError();
+    if (nepi == 16)
+        return gcap == 256 ? launch_tcs_one<256, 16>(maps, args, d16, grid, stream)
+                           : launch_tcs_one<512, 16>(maps, args, d16, grid, stream);
+    return gcap == 256 ? launch_tcs_one<256, 8>(maps, args, d16, grid, stream)
+                       : launch_tcs_one<512, 8>(maps, args, d16, grid, stream);
 }
 
 }  // namespace pqh

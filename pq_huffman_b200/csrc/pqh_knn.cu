@@ -4,17 +4,35 @@
 // reference's only call site (compute_nn_fast.c:478-481).  The host side of the
 // reference calls it once per block, serially, from its main thread, with
 // pageable malloc'ed buffers it owns; the context below is
-// created on first use and keeps streams, device buffers and workspace alive
-// across those calls.  There is no CPU fallback: without a usable sm_100 device
-// every entry point fails (knn_full_thread: message + exit(1), the reference's
-// error convention, compute_nn_fast.c:154-156).
+// created on first use and keeps streams, pinned staging rings, the NCCL
+// communicators, device buffers and workspace alive across those calls.
+// There is no CPU fallback: without a usable sm_100 device every entry point
+// fails (knn_full_thread: message + exit(1), the reference's error convention,
+// compute_nn_fast.c:154-156).
+//
+// Host memory.  The caller's buffers are pageable (block_t.data is realloc'ed,
+// fast_nn_block.c:41-66; result_data_t is malloc'ed, fast_nn_result_data.c:26-35).
+// A cudaMemcpyAsync from pageable memory is staged by the driver through one bounce
+// buffer at ~10 GB/s; here a few helper threads per device copy chunks into their own
+// pinned double buffers and issue the DMA themselves, so the host memcpy of chunk i+1
+// overlaps the DMA of chunk i and the link, not one core's memcpy, sets the pace.
+// Pinned callers (cudaHostAlloc / pqh_knn_host_alloc) are detected and copied directly.
+//
+// Several devices.  Query rows are split evenly over the devices of the context
+// (SURVEY.md 8e).  Every device needs the whole base: each uploads 1/G of it over its
+// own PCIe link and one in-place ncclAllGather over NVLink assembles it everywhere
+// (ncclCommInitAll at context creation; libnccl.so.2 is resolved at run time).  Each
+// device then returns its rows straight into the caller's arrays.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -46,6 +64,44 @@ int fail(int code, const char *fmt, ...) {
                         __LINE__);                                                         \
     } while (0)
 
+// ---- NCCL, resolved at run time -------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok() const { return handle != nullptr; }
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string *why) {
+    if (g_nccl.ok()) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names)
+        if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) {
+        *why = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return false;
+    }
+    NcclApi a;
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!a.CommInitAll || !a.CommDestroy || !a.AllGather || !a.GetErrorString) {
+        *why = "libnccl.so.2 lacks ncclCommInitAll / ncclAllGather";
+        dlclose(h);
+        return false;
+    }
+    a.handle = h;
+    g_nccl = a;
+    return true;
+}
+
+// ---- device buffers ---------------------------------------------------------------------------
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -75,13 +131,44 @@ struct DevBuf {
     }
 };
 
+// ---- pinned staging for pageable host buffers ---------------------------------------------------
+constexpr int STAGE_THREADS = 4;             // helper threads per device and direction
+constexpr size_t STAGE_CHUNK = 8u << 20;     // bytes per pinned buffer
+struct Staging {
+    void *buf[STAGE_THREADS][2] = {};
+    cudaEvent_t ev[STAGE_THREADS][2] = {};
+    bool ready = false;
+    int init() {
+        if (ready) return PQH_OK;
+        for (int t = 0; t < STAGE_THREADS; ++t)
+            for (int j = 0; j < 2; ++j) {
+                CU_TRY(cudaHostAlloc(&buf[t][j], STAGE_CHUNK, cudaHostAllocPortable));
+                CU_TRY(cudaEventCreateWithFlags(&ev[t][j], cudaEventDisableTiming));
+            }
+        ready = true;
+        return PQH_OK;
+    }
+    void release() {
+        for (int t = 0; t < STAGE_THREADS; ++t)
+            for (int j = 0; j < 2; ++j) {
+                if (buf[t][j]) cudaFreeHost(buf[t][j]);
+                if (ev[t][j]) cudaEventDestroy(ev[t][j]);
+                buf[t][j] = nullptr;
+                ev[t][j] = nullptr;
+            }
+        ready = false;
+    }
+};
+
 struct DeviceCtx {
     int dev = -1;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t xev[2] = {nullptr, nullptr};  // exact-kernel timing
     DevBuf base, queries, assign, dis, work;
+    Staging stage;
+    ncclComm_t comm = nullptr;
     // resident data set of the block searches (pqh_knn_dataset_*)
     DevBuf dataset, block_ids;
     int ds_n = 0, ds_d = 0;
@@ -89,16 +176,19 @@ struct DeviceCtx {
 
 struct Context {
     std::vector<DeviceCtx> devs;
-    int algo = PQH_ALGO_AUTO;
+    bool nccl = false;  // communicators over all devices exist
     pqh_knn_stats_t stats;
+    std::vector<int> failed;  // rows of the last search the first tensor-core pass left open
 };
 
 std::mutex g_mu;
 // one lock per device slot: block searches on different devices run concurrently, everything
-// that touches one device's buffers is serialised (lock order: g_mu, then g_dev_mu[slot])
+// that touches one device's buffers is serialised (lock order: g_mu, then g_dev_mu[slot]).
+// Entry points hold a shared_ptr to the context for their whole duration, so pqh_knn_init /
+// pqh_knn_shutdown from another thread cannot free it under them.
 constexpr int MAX_DEVS = 16;
 std::mutex g_dev_mu[MAX_DEVS];
-Context *g_ctx = nullptr;
+std::shared_ptr<Context> g_ctx;
 int g_algo = PQH_ALGO_AUTO;
 
 int parse_env_devices(std::vector<int> &out) {
@@ -121,9 +211,12 @@ int parse_env_devices(std::vector<int> &out) {
 
 void destroy_ctx(Context *c) {
     if (!c) return;
-    for (auto &d : c->devs) {
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        DeviceCtx &d = c->devs[g];
+        std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);
         if (cudaSetDevice(d.dev) != cudaSuccess) continue;
         if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.comm && g_nccl.ok()) g_nccl.CommDestroy(d.comm);
         d.base.release();
         d.queries.release();
         d.assign.release();
@@ -131,16 +224,17 @@ void destroy_ctx(Context *c) {
         d.work.release();
         d.dataset.release();
         d.block_ids.release();
+        d.stage.release();
         for (auto &e : d.ev)
             if (e) cudaEventDestroy(e);
-        for (auto &e : d.kev)
+        for (auto &e : d.xev)
             if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete c;
 }
 
-int create_ctx(const int *devices, int n, Context **out) {
+int create_ctx(const int *devices, int n, std::shared_ptr<Context> *out) {
     std::vector<int> ids;
     if (devices && n > 0) {
         ids.assign(devices, devices + n);
@@ -157,39 +251,50 @@ int create_ctx(const int *devices, int n, Context **out) {
     }
     if ((int)ids.size() > MAX_DEVS)
         return fail(PQH_EINVAL, "at most %d devices per context", MAX_DEVS);
-    Context *c = new Context();
+    pqh::tc_reload_env();  // the PQH_TC_* knobs are read here, once per context
+    std::shared_ptr<Context> c(new Context(), destroy_ctx);
     memset(&c->stats, 0, sizeof(c->stats));
     for (int id : ids) {
-        if (id < 0 || id >= count) {
-            destroy_ctx(c);
+        if (id < 0 || id >= count)
             return fail(PQH_ENODEV, "device %d requested but only %d visible", id, count);
-        }
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, id) != cudaSuccess || prop.major != 10) {
-            destroy_ctx(c);
+        if (cudaGetDeviceProperties(&prop, id) != cudaSuccess || prop.major != 10)
             return fail(PQH_ENODEV,
                         "device %d is not an sm_100 (Blackwell B200) GPU; this library ships "
                         "sm_100a code only and has no fallback",
                         id);
-        }
         DeviceCtx d;
         d.dev = id;
         d.num_sms = prop.multiProcessorCount;
         if (cudaSetDevice(id) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
-            destroy_ctx(c);
+            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess)
             return fail(PQH_ECUDA, "cannot create a stream on device %d: %s", id,
                         cudaGetErrorString(cudaGetLastError()));
-        }
         for (auto &ev : d.ev) cudaEventCreate(&ev);
-        for (auto &ev : d.kev) cudaEventCreate(&ev);
+        for (auto &ev : d.xev) cudaEventCreate(&ev);
         c->devs.push_back(d);
+    }
+    // several devices: one NCCL communicator per device, created together.
+    // $PQH_NO_NCCL=1 opts out: every device then receives the whole base over its own link.
+    const char *no_nccl = getenv("PQH_NO_NCCL");
+    if (c->devs.size() > 1 && !(no_nccl && atoi(no_nccl) != 0)) {
+        std::string why;
+        if (!load_nccl(&why)) return fail(PQH_ECOMM, "%s (set PQH_NO_NCCL=1 to run without)", why.c_str());
+        std::vector<ncclComm_t> comms(c->devs.size());
+        ncclResult_t nr = g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data());
+        if (nr != ncclSuccess)
+            return fail(PQH_ECOMM, "ncclCommInitAll over %zu devices failed: %s", ids.size(),
+                        g_nccl.GetErrorString(nr));
+        for (size_t g = 0; g < c->devs.size(); ++g) c->devs[g].comm = comms[g];
+        c->nccl = true;
     }
     *out = c;
     return PQH_OK;
 }
 
-int get_ctx(Context **out) {
+// the live context (created on first use); callers keep the shared_ptr while they work
+int get_ctx(std::shared_ptr<Context> *out) {
+    std::lock_guard<std::mutex> lock(g_mu);
     if (!g_ctx) {
         int rc = create_ctx(nullptr, 0, &g_ctx);
         if (rc) return rc;
@@ -230,12 +335,136 @@ size_t workspace_bytes(int n_rows, int nb, int d, int k, int self_join, int num_
     return align1k(pqh::tc_workspace_bytes(n_rows, nb, d, k, self_join, num_sms)) + ex + 2048;
 }
 
+// ---- host <-> device copies ---------------------------------------------------------------------
+bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Rows [0, n_rows) of a host matrix (row i at src + i * ld floats, `cols` floats used) -> dense
+// device rows at dst.  All copies are enqueued on dc.stream; returns once they are enqueued and
+// the caller's memory has been read (pageable source) or may still be in flight (pinned source).
+int h2d_rows(DeviceCtx &dc, float *dst, const float *src, size_t ld, size_t cols, size_t n_rows) {
+    if (n_rows == 0) return PQH_OK;
+    const size_t row_bytes = cols * sizeof(float);
+    if (host_is_pinned(src)) {
+        if (ld == cols)
+            CU_TRY(cudaMemcpyAsync(dst, src, n_rows * row_bytes, cudaMemcpyHostToDevice, dc.stream));
+        else
+            CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, ld * sizeof(float), row_bytes, n_rows,
+                                     cudaMemcpyHostToDevice, dc.stream));
+        return PQH_OK;
+    }
+    int rc = dc.stage.init();
+    if (rc) return rc;
+    size_t rows_per_chunk = STAGE_CHUNK / row_bytes;
+    if (rows_per_chunk == 0) {  // one row larger than a chunk: let the driver stage it
+        CU_TRY(cudaMemcpy2DAsync(dst, row_bytes, src, ld * sizeof(float), row_bytes, n_rows,
+                                 cudaMemcpyHostToDevice, dc.stream));
+        return PQH_OK;
+    }
+    const size_t n_chunks = (n_rows + rows_per_chunk - 1) / rows_per_chunk;
+    const int nt = (int)(n_chunks < (size_t)STAGE_THREADS ? n_chunks : (size_t)STAGE_THREADS);
+    std::vector<cudaError_t> errs(nt, cudaSuccess);
+    auto work = [&](int t) {
+        cudaSetDevice(dc.dev);
+        int j = 0;
+        for (size_t c = t; c < n_chunks; c += nt, j ^= 1) {
+            const size_t r0 = c * rows_per_chunk;
+            const size_t nr = n_rows - r0 < rows_per_chunk ? n_rows - r0 : rows_per_chunk;
+            cudaError_t e = cudaEventSynchronize(dc.stage.ev[t][j]);  // buffer free again?
+            char *b = static_cast<char *>(dc.stage.buf[t][j]);
+            if (ld == cols) {
+                memcpy(b, src + r0 * ld, nr * row_bytes);
+            } else {
+                for (size_t r = 0; r < nr; ++r) memcpy(b + r * row_bytes, src + (r0 + r) * ld, row_bytes);
+            }
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(dst + r0 * cols, b, nr * row_bytes, cudaMemcpyHostToDevice,
+                                    dc.stream);
+            if (e == cudaSuccess) e = cudaEventRecord(dc.stage.ev[t][j], dc.stream);
+            if (e != cudaSuccess) {
+                errs[t] = e;
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (cudaError_t e : errs)
+        if (e != cudaSuccess)
+            return fail(PQH_ECUDA, "staged host-to-device copy failed: %s", cudaGetErrorString(e));
+    return PQH_OK;
+}
+
+// Device bytes -> host.  The device data must be complete on dc.stream order (the copies are
+// enqueued there); returns when the host buffer is filled.
+int d2h_bytes(DeviceCtx &dc, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return PQH_OK;
+    if (host_is_pinned(dst)) {
+        CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dc.stream));
+        CU_TRY(cudaStreamSynchronize(dc.stream));
+        return PQH_OK;
+    }
+    int rc = dc.stage.init();
+    if (rc) return rc;
+    const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    const int nt = (int)(n_chunks < (size_t)STAGE_THREADS ? n_chunks : (size_t)STAGE_THREADS);
+    std::vector<cudaError_t> errs(nt, cudaSuccess);
+    auto work = [&](int t) {
+        cudaSetDevice(dc.dev);
+        // double-buffered: the DMA of this thread's next chunk runs while the previous one is
+        // copied out of its pinned buffer
+        size_t prev_c = (size_t)-1;
+        int j = 0;
+        auto chunk_len = [&](size_t c) {
+            const size_t off = c * STAGE_CHUNK;
+            return bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+        };
+        for (size_t c = t;; c += nt, j ^= 1) {
+            cudaError_t e = cudaSuccess;
+            if (c < n_chunks) {
+                e = cudaMemcpyAsync(dc.stage.buf[t][j], static_cast<const char *>(src) + c * STAGE_CHUNK,
+                                    chunk_len(c), cudaMemcpyDeviceToHost, dc.stream);
+                if (e == cudaSuccess) e = cudaEventRecord(dc.stage.ev[t][j], dc.stream);
+            }
+            if (e == cudaSuccess && prev_c != (size_t)-1) {
+                e = cudaEventSynchronize(dc.stage.ev[t][j ^ 1]);
+                if (e == cudaSuccess)
+                    memcpy(static_cast<char *>(dst) + prev_c * STAGE_CHUNK, dc.stage.buf[t][j ^ 1],
+                           chunk_len(prev_c));
+            }
+            if (e != cudaSuccess) {
+                errs[t] = e;
+                return;
+            }
+            if (c >= n_chunks) return;
+            prev_c = c;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (cudaError_t e : errs)
+        if (e != cudaSuccess)
+            return fail(PQH_ECUDA, "staged device-to-host copy failed: %s", cudaGetErrorString(e));
+    return PQH_OK;
+}
+
 // Search rows [q_begin,q_end) with all pointers already on device `dc`.
 // Query q's vector is row (q - q_row0) of d_v; its output row is (q - q_begin).
 int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float *d_b,
                      const float *d_v, int q_row0, int self_join, int q_begin, int q_end,
                      int *d_assign, float *d_dis, void *d_work, size_t work_bytes,
-                     cudaStream_t stream, pqh_knn_stats_t *st, bool sync_for_stats) {
+                     cudaStream_t stream, pqh_knn_stats_t *st, bool sync_for_stats,
+                     std::vector<int> *failed = nullptr) {
     const int n_rows = q_end - q_begin;
     if (n_rows <= 0 || k <= 0) return PQH_OK;
     int launches = 0;
@@ -249,7 +478,7 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
         pqh::TcTimes tt;
         CU_TRY(pqh::launch_knn_tc(d_b, d_v, q_row0, q_begin, q_begin, n_rows, nb, d, k, self_join,
                                   d_assign, d_dis, d_work, tcb, dc.num_sms, stream, &launches,
-                                  &d_fb_rows, &n_fb, dc.kev, &tt));
+                                  &d_fb_rows, &n_fb, &tt));
         if (st) {
             st->ms_prep += tt.ms_prep;
             st->ms_gemm += tt.ms_gemm;
@@ -259,29 +488,30 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
             st->inexact_operands = tt.inexact;
             st->rows_second_pass += tt.rows_pass2;
         }
+        if (failed) failed->insert(failed->end(), tt.pass1_failed.begin(), tt.pass1_failed.end());
         rows_tc = n_rows - (long long)n_fb;
         if (n_fb > 0) {
             rows_ex = n_fb;
-            CU_TRY(cudaEventRecord(dc.kev[4], stream));
+            CU_TRY(cudaEventRecord(dc.xev[0], stream));
             CU_TRY(pqh::launch_knn_exact(d_b, d_v, d_fb_rows, 0, q_row0, q_begin, (int)n_fb, nb, d,
                                          k, self_join, d_assign, d_dis,
                                          static_cast<unsigned char *>(d_work) + tcb,
                                          work_bytes - tcb, dc.num_sms, stream, &launches));
-            CU_TRY(cudaEventRecord(dc.kev[5], stream));
+            CU_TRY(cudaEventRecord(dc.xev[1], stream));
             exact_timed = true;
         }
     } else {
         rows_ex = n_rows;
-        CU_TRY(cudaEventRecord(dc.kev[4], stream));
+        CU_TRY(cudaEventRecord(dc.xev[0], stream));
         CU_TRY(pqh::launch_knn_exact(d_b, d_v, nullptr, q_begin, q_row0, q_begin, n_rows, nb, d, k,
                                      self_join, d_assign, d_dis, d_work, work_bytes, dc.num_sms,
                                      stream, &launches));
-        CU_TRY(cudaEventRecord(dc.kev[5], stream));
+        CU_TRY(cudaEventRecord(dc.xev[1], stream));
         exact_timed = true;
     }
     if (exact_timed && st && sync_for_stats) {
         CU_TRY(cudaStreamSynchronize(stream));
-        st->ms_exact += ev_ms(dc.kev[4], dc.kev[5]);
+        st->ms_exact += ev_ms(dc.xev[0], dc.xev[1]);
     }
     if (st) {
         st->rows += n_rows;
@@ -292,67 +522,81 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
     return PQH_OK;
 }
 
-// Host-pointer search on one device.
-int search_rows_host(Context *c, DeviceCtx &dc, int nq_total, int nb, int d, int k, const float *b,
-                     size_t ldb, const float *v, size_t ldv, int self_join, int q_begin, int q_end,
-                     int *assign, float *dis, pqh_knn_stats_t *st) {
+// Host-pointer search on one device of the context.  gather != null: this device is rank
+// gather->rank of gather->G devices that share the base -- it uploads only its 1/G of the base
+// rows and the others' parts arrive through ncclAllGather.
+struct GatherPlan {
+    int rank, G;
+};
+int search_rows_host(Context *c, int slot, int algo, int nq_total, int nb, int d, int k,
+                     const float *b, size_t ldb, const float *v, size_t ldv, int self_join,
+                     int q_begin, int q_end, int *assign, float *dis, const GatherPlan *gather,
+                     pqh_knn_stats_t *st, std::vector<int> *failed) {
+    DeviceCtx &dc = c->devs[slot];
     const int n_rows = q_end - q_begin;
-    if (n_rows <= 0 || k <= 0) return PQH_OK;
-    std::lock_guard<std::mutex> dev_lock(g_dev_mu[&dc - c->devs.data()]);
+    if (k <= 0) return PQH_OK;
+    if (n_rows <= 0 && !gather) return PQH_OK;
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[slot]);
     CU_TRY(cudaSetDevice(dc.dev));
-    const size_t base_bytes = (size_t)nb * d * sizeof(float);
-    const size_t out_elems = (size_t)n_rows * k;
+    // rows of the base each rank uploads (the all-gather needs equal parts: pad the buffer)
+    const size_t part = gather ? ((size_t)nb + gather->G - 1) / gather->G : (size_t)nb;
+    const size_t base_rows_alloc = gather ? part * gather->G : (size_t)nb;
+    const size_t base_bytes = base_rows_alloc * d * sizeof(float);
+    const size_t out_elems = (size_t)(n_rows > 0 ? n_rows : 0) * k;
     int rc;
     if ((rc = dc.base.ensure(base_bytes ? base_bytes : 4))) return rc;
-    if ((rc = dc.assign.ensure(out_elems * sizeof(int)))) return rc;
-    if ((rc = dc.dis.ensure(out_elems * sizeof(float)))) return rc;
-    const size_t wbytes = workspace_bytes(n_rows, nb, d, k, self_join, dc.num_sms);
-    if ((rc = dc.work.ensure(wbytes))) return rc;
+    if ((rc = dc.assign.ensure(out_elems * sizeof(int) + 4))) return rc;
+    if ((rc = dc.dis.ensure(out_elems * sizeof(float) + 4))) return rc;
+    if (n_rows > 0) {
+        const size_t wbytes = workspace_bytes(n_rows, nb, d, k, self_join, dc.num_sms);
+        if ((rc = dc.work.ensure(wbytes))) return rc;
+    }
 
     CU_TRY(cudaEventRecord(dc.ev[0], dc.stream));
-    if (base_bytes) {
-        if (ldb == (size_t)d)
-            CU_TRY(cudaMemcpyAsync(dc.base.p, b, base_bytes, cudaMemcpyHostToDevice, dc.stream));
-        else  // strided rows (e.g. an .fvecs image): the copy engine drops the padding
-            CU_TRY(cudaMemcpy2DAsync(dc.base.p, (size_t)d * sizeof(float), b, ldb * sizeof(float),
-                                     (size_t)d * sizeof(float), (size_t)nb,
-                                     cudaMemcpyHostToDevice, dc.stream));
+    float *d_b = static_cast<float *>(dc.base.p);
+    if (nb > 0) {
+        if (gather) {
+            const size_t r0 = part * gather->rank;
+            const size_t nr = r0 >= (size_t)nb ? 0 : ((size_t)nb - r0 < part ? (size_t)nb - r0 : part);
+            if ((rc = h2d_rows(dc, d_b + r0 * d, b + r0 * ldb, ldb, (size_t)d, nr))) return rc;
+            ncclResult_t nr_rc = g_nccl.AllGather(d_b + r0 * d, d_b, part * d, ncclFloat, dc.comm,
+                                                  dc.stream);
+            if (nr_rc != ncclSuccess)
+                return fail(PQH_ECOMM, "ncclAllGather of the base failed on device %d: %s", dc.dev,
+                            g_nccl.GetErrorString(nr_rc));
+        } else {
+            if ((rc = h2d_rows(dc, d_b, b, ldb, (size_t)d, (size_t)nb))) return rc;
+        }
     }
-    const float *d_b = static_cast<const float *>(dc.base.p);
     const float *d_v = d_b;
     int q_row0 = 0;
-    if (!self_join) {
+    if (!self_join && n_rows > 0) {
         // only the rows this call searches travel: row (q - q_begin) of the device copy
         const size_t qbytes = (size_t)n_rows * d * sizeof(float);
         if ((rc = dc.queries.ensure(qbytes))) return rc;
-        if (ldv == (size_t)d)
-            CU_TRY(cudaMemcpyAsync(dc.queries.p, v + (size_t)q_begin * d, qbytes,
-                                   cudaMemcpyHostToDevice, dc.stream));
-        else
-            CU_TRY(cudaMemcpy2DAsync(dc.queries.p, (size_t)d * sizeof(float),
-                                     v + (size_t)q_begin * ldv, ldv * sizeof(float),
-                                     (size_t)d * sizeof(float), (size_t)n_rows,
-                                     cudaMemcpyHostToDevice, dc.stream));
+        if ((rc = h2d_rows(dc, static_cast<float *>(dc.queries.p), v + (size_t)q_begin * ldv, ldv,
+                           (size_t)d, (size_t)n_rows)))
+            return rc;
         d_v = static_cast<const float *>(dc.queries.p);
         q_row0 = q_begin;
     }
     CU_TRY(cudaEventRecord(dc.ev[1], dc.stream));
-    rc = search_on_device(dc, c->algo, nb, d, k, d_b, d_v, q_row0, self_join, q_begin, q_end,
-                          static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
-                          dc.work.p, dc.work.cap, dc.stream, st, false);
-    if (rc) return rc;
+    if (n_rows > 0) {
+        rc = search_on_device(dc, algo, nb, d, k, d_b, d_v, q_row0, self_join, q_begin, q_end,
+                              static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
+                              dc.work.p, dc.work.cap, dc.stream, st, false, failed);
+        if (rc) return rc;
+    }
     CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
-    CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int), cudaMemcpyDeviceToHost,
-                           dc.stream));
-    CU_TRY(cudaMemcpyAsync(dis, dc.dis.p, out_elems * sizeof(float), cudaMemcpyDeviceToHost,
-                           dc.stream));
+    if ((rc = d2h_bytes(dc, assign, dc.assign.p, out_elems * sizeof(int)))) return rc;
+    if ((rc = d2h_bytes(dc, dis, dc.dis.p, out_elems * sizeof(float)))) return rc;
     CU_TRY(cudaEventRecord(dc.ev[3], dc.stream));
     CU_TRY(cudaStreamSynchronize(dc.stream));
     if (st) {
         st->ms_h2d += ev_ms(dc.ev[0], dc.ev[1]);
         st->ms_kernels += ev_ms(dc.ev[1], dc.ev[2]);
         st->ms_d2h += ev_ms(dc.ev[2], dc.ev[3]);
-        if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.kev[4], dc.kev[5]);
+        if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.xev[0], dc.xev[1]);
     }
     return PQH_OK;
 }
@@ -377,9 +621,11 @@ __global__ void gather_block_rows_kernel(const float *__restrict__ data, const i
     }
 }
 
-// Self-join among rows `row_ids` of the data set resident on `dc` (host pointers in and out).
-int dataset_search_block(Context *c, DeviceCtx &dc, int m, const int *row_ids, int k, int *assign,
-                         float *dis, pqh_knn_stats_t *st) {
+// Self-join among rows `row_ids` of the data set resident on device slot `slot` (host pointers
+// in and out).
+int dataset_search_block(Context *c, int slot, int algo, int m, const int *row_ids, int k,
+                         int *assign, float *dis, pqh_knn_stats_t *st) {
+    DeviceCtx &dc = c->devs[slot];
     if (m <= 0 || k <= 0) return PQH_OK;
     const int d = dc.ds_d;
     CU_TRY(cudaSetDevice(dc.dev));
@@ -403,9 +649,9 @@ int dataset_search_block(Context *c, DeviceCtx &dc, int m, const int *row_ids, i
         blk);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(dc.ev[1], dc.stream));
-    rc = search_on_device(dc, c->algo, m, d, k, blk, blk, 0, 1, 0, m,
-                          static_cast<int *>(dc.assign.p), static_cast<float *>(dc.dis.p),
-                          dc.work.p, dc.work.cap, dc.stream, st, false);
+    rc = search_on_device(dc, algo, m, d, k, blk, blk, 0, 1, 0, m, static_cast<int *>(dc.assign.p),
+                          static_cast<float *>(dc.dis.p), dc.work.p, dc.work.cap, dc.stream, st,
+                          false);
     if (rc) return rc;
     if (st) ++st->launches;
     CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
@@ -419,9 +665,27 @@ int dataset_search_block(Context *c, DeviceCtx &dc, int m, const int *row_ids, i
         st->ms_h2d += ev_ms(dc.ev[0], dc.ev[1]);
         st->ms_kernels += ev_ms(dc.ev[1], dc.ev[2]);
         st->ms_d2h += ev_ms(dc.ev[2], dc.ev[3]);
-        if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.kev[4], dc.kev[5]);
+        if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.xev[0], dc.xev[1]);
     }
     return PQH_OK;
+}
+
+void merge_stats(pqh_knn_stats_t &st, const pqh_knn_stats_t &s) {
+    st.rows += s.rows;
+    st.rows_tensor += s.rows_tensor;
+    st.rows_exact += s.rows_exact;
+    st.rows_second_pass += s.rows_second_pass;
+    st.launches += s.launches;
+    if (s.ms_h2d > st.ms_h2d) st.ms_h2d = s.ms_h2d;
+    if (s.ms_kernels > st.ms_kernels) st.ms_kernels = s.ms_kernels;
+    if (s.ms_d2h > st.ms_d2h) st.ms_d2h = s.ms_d2h;
+    if (s.ms_prep > st.ms_prep) st.ms_prep = s.ms_prep;
+    if (s.ms_gemm > st.ms_gemm) st.ms_gemm = s.ms_gemm;
+    if (s.ms_rerank > st.ms_rerank) st.ms_rerank = s.ms_rerank;
+    if (s.ms_exact > st.ms_exact) st.ms_exact = s.ms_exact;
+    st.candidates += s.candidates;
+    if (s.eps_ratio_max > st.eps_ratio_max) st.eps_ratio_max = s.eps_ratio_max;
+    st.inexact_operands |= s.inexact_operands;
 }
 
 int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, size_t ldb, const float *v,
@@ -430,35 +694,41 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, size_t 
     if (rc) return rc;
     if (self_join && nq_total != nb)
         return fail(PQH_EINVAL, "self-join needs nq == nb (got %d, %d)", nq_total, nb);
-    std::lock_guard<std::mutex> lock(g_mu);
-    Context *c = nullptr;
-    if ((rc = get_ctx(&c))) return rc;
-    c->algo = g_algo;
+    std::shared_ptr<Context> ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    Context *c = ctx.get();
+    const int algo = g_algo;
     auto t0 = std::chrono::steady_clock::now();
     pqh_knn_stats_t st;
     memset(&st, 0, sizeof(st));
+    std::vector<int> failed;
     const int n_rows = q_end - q_begin;
     const int G = (int)c->devs.size();
-    if (G == 1 || n_rows < 2 * G) {
-        rc = search_rows_host(c, c->devs[0], nq_total, nb, d, k, b, ldb, v, ldv, self_join, q_begin,
-                              q_end, assign, dis, &st);
+    // small jobs stay on one device: a split only pays once every device gets whole rounds
+    if (G == 1 || n_rows < 2 * G || (long long)n_rows * nb < (1LL << 28)) {
+        rc = search_rows_host(c, 0, algo, nq_total, nb, d, k, b, ldb, v, ldv, self_join, q_begin,
+                              q_end, assign, dis, nullptr, &st, &failed);
     } else {
-        // query rows split evenly over the devices; each device
-        // receives the base over its own PCIe link and returns its slice.
+        // query rows split evenly over the devices; the base is uploaded in G
+        // parts and assembled on every device with one all-gather (or, without NCCL, sent whole
+        // to every device over its own PCIe link).
         std::vector<std::thread> th;
         std::vector<int> rcs(G, 0);
         std::vector<std::string> errs(G);
         std::vector<pqh_knn_stats_t> sts(G);
+        std::vector<std::vector<int>> fails(G);
         const int per = (n_rows + G - 1) / G;
         for (int g = 0; g < G; ++g) {
             memset(&sts[g], 0, sizeof(pqh_knn_stats_t));
             th.emplace_back([&, g]() {
                 int lo = q_begin + g * per, hi = lo + per;
                 if (hi > q_end) hi = q_end;
-                if (lo >= hi) return;
-                rcs[g] = search_rows_host(c, c->devs[g], nq_total, nb, d, k, b, ldb, v, ldv,
-                                          self_join, lo, hi, assign + (size_t)(lo - q_begin) * k,
-                                          dis + (size_t)(lo - q_begin) * k, &sts[g]);
+                if (lo > hi) lo = hi;
+                GatherPlan gp = {g, G};
+                rcs[g] = search_rows_host(c, g, algo, nq_total, nb, d, k, b, ldb, v, ldv, self_join,
+                                          lo, hi, assign + (size_t)(lo - q_begin) * k,
+                                          dis + (size_t)(lo - q_begin) * k, c->nccl ? &gp : nullptr,
+                                          &sts[g], &fails[g]);
                 if (rcs[g]) errs[g] = g_err;
             });
         }
@@ -468,26 +738,17 @@ int search_rows_impl(int nq_total, int nb, int d, int k, const float *b, size_t 
                 rc = rcs[g];
                 g_err = errs[g];
             }
-            st.rows += sts[g].rows;
-            st.rows_tensor += sts[g].rows_tensor;
-            st.rows_exact += sts[g].rows_exact;
-            st.rows_second_pass += sts[g].rows_second_pass;
-            st.launches += sts[g].launches;
-            if (sts[g].ms_h2d > st.ms_h2d) st.ms_h2d = sts[g].ms_h2d;
-            if (sts[g].ms_kernels > st.ms_kernels) st.ms_kernels = sts[g].ms_kernels;
-            if (sts[g].ms_d2h > st.ms_d2h) st.ms_d2h = sts[g].ms_d2h;
-            if (sts[g].ms_prep > st.ms_prep) st.ms_prep = sts[g].ms_prep;
-            if (sts[g].ms_gemm > st.ms_gemm) st.ms_gemm = sts[g].ms_gemm;
-            if (sts[g].ms_rerank > st.ms_rerank) st.ms_rerank = sts[g].ms_rerank;
-            if (sts[g].ms_exact > st.ms_exact) st.ms_exact = sts[g].ms_exact;
-            st.candidates += sts[g].candidates;
-            if (sts[g].eps_ratio_max > st.eps_ratio_max) st.eps_ratio_max = sts[g].eps_ratio_max;
-            st.inexact_operands |= sts[g].inexact_operands;
+            merge_stats(st, sts[g]);
+            failed.insert(failed.end(), fails[g].begin(), fails[g].end());
         }
     }
     st.ms_total =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    c->stats = st;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        c->stats = st;
+        c->failed.swap(failed);
+    }
     return rc;
 }
 
@@ -499,17 +760,13 @@ const char *pqh_last_error(void) { return g_err.c_str(); }
 
 int pqh_knn_init(const int *devices, int n_devices) {
     std::lock_guard<std::mutex> lock(g_mu);
-    if (g_ctx) {
-        destroy_ctx(g_ctx);
-        g_ctx = nullptr;
-    }
+    g_ctx.reset();  // a search still running on the old context keeps it alive until it returns
     return create_ctx(devices, n_devices, &g_ctx);
 }
 
 void pqh_knn_shutdown(void) {
     std::lock_guard<std::mutex> lock(g_mu);
-    destroy_ctx(g_ctx);
-    g_ctx = nullptr;
+    g_ctx.reset();
 }
 
 int pqh_knn_device_count(void) {
@@ -539,7 +796,22 @@ int pqh_knn_search_rows_ld(int nq_total, int nb, int d, int k, const float *b, l
 }
 
 long long pqh_knn_workspace_bytes(int nq, int nb, int d, int k) {
-    size_t a = workspace_bytes(nq, nb, d, k, 0, 148), b = workspace_bytes(nq, nb, d, k, 1, 148);
+    // sized for the device the search will run on: the SM count fixes the row-slice geometry
+    int sms = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (g_ctx && !g_ctx->devs.empty()) sms = g_ctx->devs[0].num_sms;
+    }
+    if (sms <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0) {
+            cudaGetLastError();
+            sms = 148;  // no device visible (header / ABI tests): a B200's count
+        }
+    }
+    size_t a = workspace_bytes(nq, nb, d, k, 0, sms), b = workspace_bytes(nq, nb, d, k, 1, sms);
     return (long long)(a > b ? a : b);
 }
 
@@ -548,14 +820,16 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
                           float *d_dis, void *d_work, long long work_bytes, void *stream) {
     int rc = check_args(nq_total, nb, d, k, d_b, d_v, q_begin, q_end, d_assign, d_dis);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(g_mu);
-    Context *c = nullptr;
-    if ((rc = get_ctx(&c))) return rc;
-    c->algo = g_algo;
-    DeviceCtx *dc = nullptr;
-    for (auto &x : c->devs)
-        if (x.dev == device) dc = &x;
-    if (!dc) return fail(PQH_EINVAL, "device %d is not part of the context", device);
+    std::shared_ptr<Context> ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    Context *c = ctx.get();
+    const int algo = g_algo;
+    int slot = -1;
+    for (size_t i = 0; i < c->devs.size(); ++i)
+        if (c->devs[i].dev == device) slot = (int)i;
+    if (slot < 0) return fail(PQH_EINVAL, "device %d is not part of the context", device);
+    DeviceCtx *dc = &c->devs[slot];
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[slot]);
     CU_TRY(cudaSetDevice(device));
     const int n_rows = q_end - q_begin;
     if (n_rows > 0 &&
@@ -565,10 +839,11 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
     pqh_knn_stats_t st;
     memset(&st, 0, sizeof(st));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dc->stream;
-    rc = search_on_device(*dc, c->algo, nb, d, k, d_b, d_v, 0, self_join, q_begin, q_end,
-                          d_assign, d_dis, d_work, (size_t)work_bytes, s, &st, stream == nullptr);
+    rc = search_on_device(*dc, algo, nb, d, k, d_b, d_v, 0, self_join, q_begin, q_end, d_assign,
+                          d_dis, d_work, (size_t)work_bytes, s, &st, stream == nullptr);
     if (rc) return rc;
     if (!stream) CU_TRY(cudaStreamSynchronize(s));
+    std::lock_guard<std::mutex> lock(g_mu);
     c->stats = st;
     return PQH_OK;
 }
@@ -576,40 +851,59 @@ int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const 
 int pqh_knn_dataset_load(int n, int d, const float *rows, long long ld) {
     if (n < 0 || d <= 0 || ld < d || (n > 0 && !rows))
         return fail(PQH_EINVAL, "bad data set n=%d d=%d ld=%lld", n, d, ld);
-    std::lock_guard<std::mutex> lock(g_mu);
-    Context *c = nullptr;
+    std::shared_ptr<Context> ctx;
     int rc;
-    if ((rc = get_ctx(&c))) return rc;
-    memset(&c->stats, 0, sizeof(c->stats));
-    for (size_t g = 0; g < c->devs.size(); ++g) {
+    if ((rc = get_ctx(&ctx))) return rc;
+    Context *c = ctx.get();
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        memset(&c->stats, 0, sizeof(c->stats));
+    }
+    // every device receives the whole set over its own link, all links at once
+    const int G = (int)c->devs.size();
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    auto load_one = [&](int g) {
         DeviceCtx &dc = c->devs[g];
         std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);
-        CU_TRY(cudaSetDevice(dc.dev));
-        const size_t bytes = (size_t)n * d * sizeof(float);
-        if ((rc = dc.dataset.ensure(bytes ? bytes : 4))) return rc;
-        if (bytes)
-            CU_TRY(cudaMemcpy2DAsync(dc.dataset.p, (size_t)d * sizeof(float), rows,
-                                     (size_t)ld * sizeof(float), (size_t)d * sizeof(float),
-                                     (size_t)n, cudaMemcpyHostToDevice, dc.stream));
-        dc.ds_n = n;
-        dc.ds_d = d;
-    }
-    for (auto &dc : c->devs) {
-        CU_TRY(cudaSetDevice(dc.dev));
-        CU_TRY(cudaStreamSynchronize(dc.stream));
-    }
+        auto run = [&]() -> int {
+            CU_TRY(cudaSetDevice(dc.dev));
+            const size_t bytes = (size_t)n * d * sizeof(float);
+            int r;
+            if ((r = dc.dataset.ensure(bytes ? bytes : 4))) return r;
+            if ((r = h2d_rows(dc, static_cast<float *>(dc.dataset.p), rows, (size_t)ld, (size_t)d,
+                              (size_t)n)))
+                return r;
+            CU_TRY(cudaStreamSynchronize(dc.stream));
+            dc.ds_n = n;
+            dc.ds_d = d;
+            return PQH_OK;
+        };
+        rcs[g] = run();
+        if (rcs[g]) errs[g] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; ++g) th.emplace_back(load_one, g);
+    load_one(0);
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) {
+            g_err = errs[g];
+            return rcs[g];
+        }
     return PQH_OK;
 }
 
 int pqh_knn_dataset_search_block(int slot, int m, const int *row_ids, int k, int *assign,
                                  float *dis) {
-    Context *c = nullptr;
+    std::shared_ptr<Context> ctx;
     int algo;
     {
         std::lock_guard<std::mutex> lock(g_mu);
-        c = g_ctx;
+        ctx = g_ctx;
         algo = g_algo;
     }
+    Context *c = ctx.get();
     if (!c) return fail(PQH_EINVAL, "no data set loaded");
     if (slot < 0 || slot >= (int)c->devs.size())
         return fail(PQH_EINVAL, "device slot %d out of range (context has %zu)", slot,
@@ -628,8 +922,7 @@ int pqh_knn_dataset_search_block(int slot, int m, const int *row_ids, int k, int
             if (row_ids[i] < 0 || row_ids[i] >= dc.ds_n)
                 return fail(PQH_EINVAL, "row id %d at position %d outside the data set (%d rows)",
                             row_ids[i], i, dc.ds_n);
-        c->algo = algo;
-        rc = dataset_search_block(c, dc, m, row_ids, k, assign, dis, &st);
+        rc = dataset_search_block(c, slot, algo, m, row_ids, k, assign, dis, &st);
     }
     const double ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -655,11 +948,15 @@ int pqh_knn_dataset_search_block(int slot, int m, const int *row_ids, int k, int
 }
 
 void pqh_knn_dataset_release(void) {
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_ctx) return;
-    for (size_t g = 0; g < g_ctx->devs.size(); ++g) {
-        std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);
-        DeviceCtx &dc = g_ctx->devs[g];
+    std::shared_ptr<Context> ctx;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        ctx = g_ctx;
+    }
+    if (!ctx) return;
+    for (size_t g = 0; g < ctx->devs.size(); ++g) {
+        std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);  // waits for a search on that device
+        DeviceCtx &dc = ctx->devs[g];
         if (cudaSetDevice(dc.dev) != cudaSuccess) continue;
         cudaStreamSynchronize(dc.stream);
         dc.dataset.release();
@@ -672,10 +969,9 @@ void *pqh_knn_host_alloc(long long bytes) {
     void *p = nullptr;
     if (bytes <= 0) return nullptr;
     {
-        std::lock_guard<std::mutex> lock(g_mu);
-        Context *c = nullptr;
-        if (get_ctx(&c)) return nullptr;
-        cudaSetDevice(c->devs[0].dev);
+        std::shared_ptr<Context> ctx;
+        if (get_ctx(&ctx)) return nullptr;
+        cudaSetDevice(ctx->devs[0].dev);
     }
     if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
@@ -695,6 +991,14 @@ int pqh_knn_last_stats(pqh_knn_stats_t *out) {
     if (!g_ctx) return fail(PQH_EINVAL, "no context");
     *out = g_ctx->stats;
     return PQH_OK;
+}
+
+int pqh_knn_last_fallback_rows(int *rows, int capacity) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx) return 0;
+    const int n = (int)g_ctx->failed.size();
+    for (int i = 0; i < n && i < capacity; ++i) rows[i] = g_ctx->failed[i];
+    return n;
 }
 
 void knn_full_thread(int distance_type, int nq, int nb, int d, int k, const float *b,

@@ -34,6 +34,7 @@
 #include <limits.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -98,7 +99,7 @@ static options_t parse(int argc, char **argv) {
     o.delete_temp = 1;
     o.init_temp = 1;
     o.with_blocks_stat = 0;
-    o.num_threads = 1;
+    o.num_threads = 0; /* 0: flag absent -> every core this process may run on */
     o.blocks_info_cache = NULL;
     o.blocks_per_dim = 3;
     o.overlap = 0.3;
@@ -136,7 +137,7 @@ static options_t parse(int argc, char **argv) {
         fprintf(stderr, "num_nn must be >= 1\n");
         exit(1);
     }
-    if (o.num_threads < 1) o.num_threads = 1;
+    if (o.num_threads < 0) o.num_threads = 0;
     return o;
 }
 
@@ -260,6 +261,7 @@ static void merge_block_part(int t, int nt, void *arg) {
         const float *di = a->dis + (size_t)r * k1;
         for (int c = 1; c < k1; ++c) {
             slot_t x;
+            if (ai[c] < 0) continue; /* unfilled tail of a row (k > block size): no neighbour */
             x.id = (uint32_t)(a->row_ids ? a->row_ids[ai[c]] : ai[c]);
             x.dist = di[c];
             offer(heap, k, x);
@@ -484,9 +486,16 @@ int main(int argc, char **argv) {
     const double t_read = now_s();
 
     const int k = o.num_nn;
+    /* host threads (row finding, merges): an explicit --num-threads is honoured, as the
+     * reference hands it to knn_full_thread as the thread budget (compute_nn_fast.c:481);
+     * without the flag every core of the affinity mask is used (cpusets count, not the box) */
     int nt = o.num_threads;
-    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-    if (nt < ncpu) nt = (int)(ncpu > 64 ? 64 : ncpu); /* the host side is ours: use the cores */
+    if (nt <= 0) {
+        cpu_set_t set;
+        long ncpu = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set)
+                                                                : sysconf(_SC_NPROCESSORS_ONLN);
+        nt = (int)(ncpu > 64 ? 64 : (ncpu < 1 ? 1 : ncpu));
+    }
     if (nt > n) nt = n > 0 ? (int)n : 1;
 
     /* ---- the heaps: fresh, or as an earlier run left them in the temp file ---- */

@@ -48,6 +48,16 @@ def last_stats():
     return {name: getattr(st, name) for name, _ in _lib.Stats._fields_}
 
 
+def last_fallback_rows():
+    """Query rows of the last host-pointer search that the first tensor-core pass could not
+    certify (redone by the second pass or the exact kernel): a test hook."""
+    lib = _lib.load()
+    n = lib.pqh_knn_last_fallback_rows(None, 0)
+    out = np.empty(max(n, 1), dtype=np.int32)
+    n = min(n, lib.pqh_knn_last_fallback_rows(out.ctypes.data, out.size))
+    return out[:n]
+
+
 def _as_f32(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     if a.ndim != 2:

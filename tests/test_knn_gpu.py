@@ -126,12 +126,12 @@ def test_mixed_certified_and_fallback_rows(oracle):
 @pytest.mark.parametrize("gen,n,d,k", [("sift", 6000, 128, 17), ("gist", 4000, 960, 17),
                                        ("deep", 6000, 96, 33), ("uniform", 5000, 272, 9),
                                        ("gist", 5000, 100, 17)])
-def test_certificate_error_bound_dominates_real_error(monkeypatch, gen, n, d, k):
+def test_certificate_error_bound_dominates_real_error(tc_env, gen, n, d, k):
     """The certificate assumes |tensor score - true score| <= eps (FP16 rounding + the tensor
     core's FP32 accumulation).  Measure the real error of every candidate score against an FP64
     dot product on the device and check that the bound holds with room to spare."""
-    monkeypatch.setenv("PQH_TC_CHECK_EPS", "1")
-    monkeypatch.setenv("PQH_TC_I8", "0")    # this test is about the FP16 path, also for uint8 data
+    # this test is about the FP16 path, also for uint8 data
+    tc_env(PQH_TC_CHECK_EPS=1, PQH_TC_I8=0)
     x = {"sift": synth.sift_like, "gist": synth.gist_like, "deep": synth.deep_like,
          "uniform": synth.uniform}[gen](n, d, seed=7 * n + d)
     knn.knn_full_thread(x, None, k)
@@ -187,17 +187,63 @@ def test_tensor_path_boundaries(oracle, n, d, k):
     assert_rows_equal(got, oracle.knn(x, None, k))
 
 
-@pytest.mark.parametrize("variant", ["2", "3", "4", "5"])
-def test_experimental_kernel_variants_stay_exact(monkeypatch, oracle, variant):
-    """The A/B variants kept in the tree (CTA-pair kernels, streaming kernel forced on a small d,
-    query operand in tensor memory) must keep producing the oracle's answer."""
-    monkeypatch.setenv("PQH_TC_VARIANT", variant)
-    x = synth.sift_like(6000, 128, seed=77)
-    got = knn.knn_full_thread(x, None, 17)
+KNOBS = [
+    dict(PQH_TC_EPI=16),
+    dict(PQH_TC_MMA=2),
+    dict(PQH_TC_EPI=16, PQH_TC_MMA=2),
+    dict(PQH_TC_ORDER=0),
+    dict(PQH_TC_ORDER=0, PQH_TC_EPI=16),
+    dict(PQH_TC_STREAM=1),
+    dict(PQH_TC_STREAM=1, PQH_TC_EPI=16),
+    dict(PQH_TC_I8=0, PQH_TC_EPI=16, PQH_TC_MMA=2),
+    dict(PQH_TC_SLICE_MB=64),
+]
+
+
+_KNOB_CASES = {}
+
+
+def _knob_cases(oracle):
+    """Inputs and oracle answers shared by every configuration (computed once)."""
+    if not _KNOB_CASES:
+        x = synth.with_duplicates_and_ties(synth.sift_like(20000, 128, seed=77), n_dups=6, n_ties=6)
+        g = synth.gist_like(9000, 96, seed=78)
+        b = synth.deep_like(9000, 96, seed=79)
+        v = synth.deep_like(700, 96, seed=80)
+        _KNOB_CASES.update(x=x, g=g, b=b, v=v, ex=oracle.knn(x, None, 17), eg=oracle.knn(g, None, 9),
+                           ebv=oracle.knn(b, v, 33))
+    return _KNOB_CASES
+
+
+@pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a[7:]}={b}" for a, b in k.items()))
+def test_kernel_configurations_stay_exact(tc_env, oracle, knobs):
+    """Every selectable configuration of the tensor-core path -- 8 or 16 filter warps, one or two
+    MMA issuers, locality order on or off, the streaming kernel forced on a small d, small row
+    slices -- must produce the oracle's answer: the knobs only decide how fast."""
+    c = _knob_cases(oracle)
+    tc_env(**knobs)
+    got = knn.knn_full_thread(c["x"], None, 17)
     assert knn.last_stats()["rows_tensor"] > 0
-    assert_rows_equal(got, oracle.knn(x, None, 17))
-    g = synth.gist_like(4000, 96, seed=78)
-    assert_rows_equal(knn.knn_full_thread(g, None, 9), oracle.knn(g, None, 9))
+    assert_rows_equal(got, c["ex"])
+    assert_rows_equal(knn.knn_full_thread(c["g"], None, 9), c["eg"])
+    assert_rows_equal(knn.knn_full_thread(c["b"], c["v"], 33), c["ebv"])
+    a, dd = knn.search_rows(c["x"], None, 17, 5000, 12345)
+    assert_rows_equal((a, dd), (c["ex"][0][5000:12345], c["ex"][1][5000:12345]))
+
+
+def test_row_slices_bound_the_scratch(tc_env, oracle):
+    """The first pass runs in row slices so that the candidate lists never exceed the budget
+    ($PQH_TC_SLICE_MB); the workspace the library asks for must stay bounded as n grows."""
+    tc_env(PQH_TC_SLICE_MB=64)
+    x = synth.sift_like(90000, 64, seed=5)
+    got = knn.knn_full_thread(x, None, 17)
+    rows = np.random.default_rng(1).choice(90000, 48, replace=False)
+    for r in rows:
+        ea, ed = oracle.knn_rows(x, None, 17, int(r), int(r) + 1)
+        assert np.array_equal(got[0][r], ea[0]) and np.array_equal(got[1][r], ed[0])
+    tc_env(PQH_TC_SLICE_MB=None)
+    # Deep10M-shaped: operands 1.9 GB + lists of one slice, not 41 GB of lists
+    assert knn.workspace_bytes(10_000_000, 10_000_000, 96, 33) <= 8 * 2**30
 
 
 def test_mass_duplicates_through_tensor_path(oracle):
@@ -348,7 +394,7 @@ def test_resident_dataset_blocks_on_two_gpus_concurrently(oracle):
         assert_rows_equal(got, oracle.knn(x[ids], None, k))
 
 
-def test_integer_tensor_path(monkeypatch, oracle):
+def test_integer_tensor_path(tc_env, oracle):
     """uint8-valued data (SIFT-shaped) takes the exact INT8 tensor-core path (stats:
     inexact_operands == 2), PQH_TC_I8=0 keeps it on the FP16 path; data the 8-bit operands or the
     fold columns cannot hold falls back to FP16 by itself.  Same bits either way."""
@@ -356,10 +402,10 @@ def test_integer_tensor_path(monkeypatch, oracle):
     exp = oracle.knn(x, None, 17)
     assert_rows_equal(knn.knn_full_thread(x, None, 17), exp)
     assert knn.last_stats()["inexact_operands"] == 2
-    monkeypatch.setenv("PQH_TC_I8", "0")
+    tc_env(PQH_TC_I8=0)
     assert_rows_equal(knn.knn_full_thread(x, None, 17), exp)
     assert knn.last_stats()["inexact_operands"] == 0
-    monkeypatch.delenv("PQH_TC_I8")
+    tc_env(PQH_TC_I8=None)
     # distinct queries, ragged sizes, odd dimension (padding to 32-byte K steps)
     b = synth.sift_like(5000, 100, seed=32)
     v = synth.sift_like(777, 100, seed=33)

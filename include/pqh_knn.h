@@ -153,6 +153,37 @@ void *pqh_knn_host_alloc(long long bytes);
 void pqh_knn_host_free(void *p);
 
 /*
+ * Device-side merge of the partitioned mode.  The reference merges every searched block into
+ * per-vector k-slot max-heaps kept in its temp file (run_merge_block, compute_nn_fast.c:485-508;
+ * fast_nn_heap_push, fast_nn_temp_file.c:11-54: an item is dropped unless strictly nearer than
+ * the current worst, or if its id is already present) and heap-sorts them at the end
+ * (temp_file_to_result / fast_nn_heap_sort, fast_nn_temp_file.c:56-63,253-301).  Here the heaps
+ * live in HBM (device slot 0) and a block's result never travels to the host:
+ *
+ *   pqh_knn_heaps_create               n heaps of k items {uint32 index, float dist}
+ *                                      (nn_item_t, fast_nn_temp_file.h:11-14); image = the bytes
+ *                                      of an existing temp file (--no-init-temp-file) or NULL for
+ *                                      fresh heaps {UINT_MAX, +inf} (init_temp_file, :83-129)
+ *   pqh_knn_dataset_search_block_merge pqh_knn_dataset_search_block + run_merge_block on the
+ *                                      device.  `ticket` numbers the blocks 0, 1, 2, ... in the
+ *                                      order the reference's serial loop would merge them: the
+ *                                      searches may run concurrently on different slots, the
+ *                                      merges are applied in ticket order (a call waits for its
+ *                                      turn; every ticket must be used exactly once).  Blocks of
+ *                                      fewer than two rows only take their turn.
+ *   pqh_knn_heaps_export               image (n*k items, may be NULL): the heap array as the temp
+ *                                      file holds it; ids/dists (n*k each, may both be NULL): the
+ *                                      heap-sorted rows as nn_indices.ivecsl / nn_dist.fvecsl
+ *                                      hold them (unfilled slots 0xFFFFFFFF / +inf)
+ *   pqh_knn_heaps_release              frees them
+ */
+int pqh_knn_heaps_create(long long n, int k, const void *image);
+int pqh_knn_dataset_search_block_merge(int slot, int m, const int *row_ids, int k1,
+                                       long long ticket);
+int pqh_knn_heaps_export(void *image, unsigned *ids, float *dists);
+void pqh_knn_heaps_release(void);
+
+/*
  * Counters of the last search on this thread's context, for tests and
  * bench.py: how the rows were resolved and how many kernels were launched.
  */

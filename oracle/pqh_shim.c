@@ -6,6 +6,8 @@
  * the CPU test suite (tests/test_host_cli_cpu.py).  Linked only into
  * oracle/lib/pqh_compute_nn_fast_shim; the product binary links libpqh_knn.so and has no CPU path.
  */
+#include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -70,4 +72,102 @@ int pqh_knn_search_rows_ld(int nq_total, int nb, int d, int k, const float *b, l
     knn_full_thread(2, nb, nb, d, k, x, x, NULL, assign, dis, 4);
     free(x);
     return PQH_OK;
+}
+
+/* ---- device-side merge API, on the CPU: the reference's heap rules restated once more
+ * (fast_nn_temp_file.c:11-63, compute_nn_fast.c:485-508) so that the driver's ticket-ordered,
+ * result-stays-on-the-device flow can be held against the reference's binary without a GPU ---- */
+typedef struct {
+    unsigned id;
+    float dist;
+} item_t;
+static item_t *g_heaps;
+static long long g_hn, g_ticket;
+static int g_hk;
+static pthread_mutex_t g_hmu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_hcv = PTHREAD_COND_INITIALIZER;
+
+static void sink(item_t *heap, int n, item_t x) {
+    int hole = 0;
+    for (;;) {
+        int left = 2 * hole + 1, right = left + 1, pick = -1;
+        if (right < n && heap[right].dist > heap[left].dist && heap[right].dist > x.dist) pick = right;
+        else if (left < n && heap[left].dist > x.dist) pick = left;
+        if (pick < 0) break;
+        heap[hole] = heap[pick];
+        hole = pick;
+    }
+    heap[hole] = x;
+}
+
+int pqh_knn_heaps_create(long long n, int k, const void *image) {
+    free(g_heaps);
+    g_heaps = (item_t *)malloc(sizeof(item_t) * (size_t)(n * k + 1));
+    g_hn = n;
+    g_hk = k;
+    g_ticket = 0;
+    if (image) {
+        memcpy(g_heaps, image, sizeof(item_t) * (size_t)(n * k));
+    } else {
+        for (long long i = 0; i < n * k; ++i) {
+            g_heaps[i].id = 0xFFFFFFFFu;
+            g_heaps[i].dist = INFINITY;
+        }
+    }
+    return PQH_OK;
+}
+
+int pqh_knn_dataset_search_block_merge(int slot, int m, const int *row_ids, int k1,
+                                       long long ticket) {
+    int *assign = NULL;
+    float *dis = NULL;
+    if (m > 1 && k1 > 1) {
+        assign = (int *)malloc(sizeof(int) * (size_t)m * k1);
+        dis = (float *)malloc(sizeof(float) * (size_t)m * k1);
+        pqh_knn_dataset_search_block(slot, m, row_ids, k1, assign, dis);
+    }
+    pthread_mutex_lock(&g_hmu);
+    while (g_ticket != ticket) pthread_cond_wait(&g_hcv, &g_hmu);
+    if (assign) {
+        for (int r = 0; r < m; ++r) {
+            item_t *heap = g_heaps + (size_t)row_ids[r] * g_hk;
+            for (int c = 1; c < k1; ++c) {
+                const int a = assign[(size_t)r * k1 + c];
+                if (a < 0) continue;
+                item_t x = {(unsigned)row_ids[a], dis[(size_t)r * k1 + c]};
+                int present = 0;
+                if (x.dist >= heap[0].dist) continue;
+                for (int i = 0; i < g_hk; ++i) present |= heap[i].id == x.id;
+                if (!present) sink(heap, g_hk, x);
+            }
+        }
+    }
+    ++g_ticket;
+    pthread_cond_broadcast(&g_hcv);
+    pthread_mutex_unlock(&g_hmu);
+    free(assign);
+    free(dis);
+    return PQH_OK;
+}
+
+int pqh_knn_heaps_export(void *image, unsigned *ids, float *dists) {
+    if (image) memcpy(image, g_heaps, sizeof(item_t) * (size_t)(g_hn * g_hk));
+    if (ids && dists) {
+        item_t *w = (item_t *)malloc(sizeof(item_t) * (size_t)(g_hk + 1));
+        for (long long r = 0; r < g_hn; ++r) {
+            memcpy(w, g_heaps + (size_t)r * g_hk, sizeof(item_t) * (size_t)g_hk);
+            for (int n = g_hk - 1; n >= 0; --n) {
+                ids[(size_t)r * g_hk + n] = w[0].id;
+                dists[(size_t)r * g_hk + n] = w[0].dist;
+                sink(w, n, w[n]);
+            }
+        }
+        free(w);
+    }
+    return PQH_OK;
+}
+
+void pqh_knn_heaps_release(void) {
+    free(g_heaps);
+    g_heaps = NULL;
 }

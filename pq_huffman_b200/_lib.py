@@ -22,6 +22,10 @@ EXPORTS = (
     "pqh_knn_dataset_load",
     "pqh_knn_dataset_search_block",
     "pqh_knn_dataset_release",
+    "pqh_knn_heaps_create",
+    "pqh_knn_dataset_search_block_merge",
+    "pqh_knn_heaps_export",
+    "pqh_knn_heaps_release",
     "pqh_knn_host_alloc",
     "pqh_knn_host_free",
 )
@@ -96,6 +100,14 @@ def load():
     lib.pqh_knn_dataset_load.restype = C.c_int
     lib.pqh_knn_dataset_search_block.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, vp]
     lib.pqh_knn_dataset_search_block.restype = C.c_int
+    lib.pqh_knn_heaps_create.argtypes = [C.c_longlong, C.c_int, vp]
+    lib.pqh_knn_heaps_create.restype = C.c_int
+    lib.pqh_knn_dataset_search_block_merge.argtypes = [C.c_int, C.c_int, vp, C.c_int, C.c_longlong]
+    lib.pqh_knn_dataset_search_block_merge.restype = C.c_int
+    lib.pqh_knn_heaps_export.argtypes = [vp, vp, vp]
+    lib.pqh_knn_heaps_export.restype = C.c_int
+    lib.pqh_knn_heaps_release.argtypes = []
+    lib.pqh_knn_heaps_release.restype = None
     lib.pqh_knn_dataset_release.argtypes = []
     lib.pqh_knn_dataset_release.restype = None
     lib.pqh_knn_host_alloc.argtypes = [C.c_longlong]

@@ -63,6 +63,6 @@ cudaError_t launch_order_self_of(const int *d_ids, int n, const int *base_inv, i
 
 // ---- knn_tcs.cu (streaming kernel for large d) ----
 cudaError_t launch_tcs(const void *maps, const void *args, int gcap, int d16, int n_items,
-                       int num_sms, int nepi, cudaStream_t stream);
+                       int num_sms, cudaStream_t stream);
 
 }  // namespace pqh

@@ -16,6 +16,8 @@
 // base operand; the re-rank kernel maps them back (base_perm) before it orders ties.
 //
 // Cost: n x C x 32 FMAs + three passes over n integers (1M x 128: 1024 cells, < 2 ms).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "knn_tc_common.cuh"
 
@@ -23,8 +25,8 @@ namespace pqh {
 
 namespace {
 
-constexpr int ORD_DSUB = 32;       // coordinates sampled for the cell assignment
-constexpr int ORD_PCHUNK = 128;    // pivots per shared-memory chunk
+constexpr int ORD_DSUB = 128;      // coordinates used for the cell assignment (sampled if d is larger)
+constexpr int ORD_PCHUNK = 64;     // pivots per shared-memory chunk
 constexpr int ORD_MAX_CELLS = 4096;
 
 // pivot c = base row (c + 1/2) * nb / C, restricted to the sampled coordinates; pn[c] = |p|^2
@@ -45,7 +47,7 @@ __global__ void order_pivots_kernel(const float *__restrict__ base, int nb, int 
 
 // cell[i] = argmin_c |x_i - p_c|^2 over the sampled coordinates (= argmin |p|^2 - 2 x.p);
 // hist[cell]++.  One thread per row, the pivots streamed through shared memory.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 order_assign_kernel(const float *__restrict__ x, int n, int d, int dsub, int C,
                     const float *__restrict__ piv, const float *__restrict__ pn,
                     int *__restrict__ cell, int *__restrict__ hist) {
@@ -169,6 +171,11 @@ size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
 int order_num_cells(int nb) {
+    static const int forced = [] {
+        const char *e = getenv("PQH_TC_CELLS");  // experiments
+        return e ? atoi(e) : 0;
+    }();
+    if (forced >= 16 && forced <= ORD_MAX_CELLS) return forced;
     int c = 16;
     while (c < ORD_MAX_CELLS && (long long)c * 1024 < nb) c *= 2;
     return c;
@@ -196,7 +203,12 @@ struct OrderWork {
 OrderWork carve(void *d_work, int slice_rows, int nb, int d, int slice_qtiles) {
     OrderWork w;
     w.C = order_num_cells(nb);
+    static const int forced_dims = [] {
+        const char *e = getenv("PQH_TC_ODIMS");  // experiments
+        return e ? atoi(e) : 0;
+    }();
     w.dsub = d < ORD_DSUB ? d : ORD_DSUB;
+    if (forced_dims >= 1 && forced_dims < w.dsub) w.dsub = forced_dims;
     unsigned char *p = reinterpret_cast<unsigned char *>(((uintptr_t)d_work + 255) & ~(uintptr_t)255);
     auto take = [&](size_t bytes) {
         void *r = p;
@@ -234,7 +246,7 @@ cudaError_t launch_order_base(const float *d_base, int nb, int d, int slice_rows
         return e;
     order_pivots_kernel<<<(w.C + 127) / 128, 128, 0, stream>>>(d_base, nb, d, w.dsub, w.C, w.piv,
                                                                w.pn);
-    order_assign_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(d_base, nb, d, w.dsub, w.C, w.piv,
+    order_assign_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d_base, nb, d, w.dsub, w.C, w.piv,
                                                               w.pn, w.cell_b, w.hist_b);
     order_scan_kernel<<<1, 1024, 0, stream>>>(w.hist_b, w.C, w.start_b, w.cur_b);
     order_scatter_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(w.cell_b, nb, 0, w.cur_b,
@@ -265,7 +277,7 @@ cudaError_t launch_order_queries(const float *d_queries, int q_begin, int n_rows
         cq = w.cell_b + q_begin;
         order_count_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(cq, n_rows, w.hist_q);
     } else {
-        order_assign_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(
+        order_assign_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(
             d_queries, n_rows, d, w.dsub, w.C, w.piv, w.pn, w.cell_q, w.hist_q);
     }
     order_scan_kernel<<<1, 1024, 0, stream>>>(w.hist_q, w.C, w.start_q, w.cur_q);

@@ -52,13 +52,14 @@ namespace {
 struct TcEnv {
     int i8 = 1;        // PQH_TC_I8: integer tensor-core path for uint8-valued data
     int order = 1;     // PQH_TC_ORDER: locality order of the sweep (knn_order.cu)
-    int nepi = 8;      // PQH_TC_EPI: filter warps per CTA, 8 or 16
     int nmma = 1;      // PQH_TC_MMA: MMA-issuing threads per CTA, 1 or 2
+    int early = 0;     // PQH_TC_EARLY: release the accumulator stage before filtering
     int l_exact = 0, l_inexact = 0;  // PQH_TC_LEXACT / PQH_TC_LINEXACT: candidates kept per row
     int gcap = 0;      // PQH_TC_GCAP: list capacity, 256 or 512
     int nsplit = 0;    // PQH_TC_NSPLIT: base splits
     int no_tail = 0, no_pass2 = 0, check_eps = 0;
-    int debug = 0;     // PQH_TC_DEBUG: 1 = MMA only, 2 = no slow path (timing experiments)
+    int debug = 0;     // PQH_TC_DEBUG: 1 = MMA only, 2 = no slow path (timing experiments),
+                       // 3 = normal run + counters printed
     int streaming = 0; // PQH_TC_STREAM=1: streaming kernel for every d
     int slice_mb = 2048;  // PQH_TC_SLICE_MB: candidate-list scratch per row slice
     bool loaded = false;
@@ -237,13 +238,12 @@ __device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *
 }
 
 // Warp roles: warp 0 = TMA producer, warps 1 .. NMMA = MMA issuers (one elected thread each),
-// then NEPI filter warps.  With NMMA == 2 the two issuers take alternate steps (issuer m fills
+// then the 8 filter warps.  With NMMA == 2 the two issuers take alternate steps (issuer m fills
 // accumulator stage m), so the barrier round trips of one overlap the MMAs of the other.
 // Steps are numbered over the life of the CTA: B ring stage = step % 4, accumulator stage =
 // step & 1.
-template <int GCAP, bool I8, int NEPI, int NMMA>
-__global__ void __launch_bounds__(tc_threads(NEPI) + (NMMA - 1) * 32, 1)
-__maxnreg__(tc_max_regs(tc_threads(NEPI) + (NMMA - 1) * 32))
+template <int GCAP, bool I8, int NMMA, bool EARLY>
+__global__ void __launch_bounds__(tc_threads(NMMA), 1)
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -252,7 +252,6 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     uint8_t *smA = smem;
     uint8_t *smB = smA + plan.a_bytes;
     TcSmemTail &tail = *reinterpret_cast<TcSmemTail *>(smB + TC_NSTAGE * plan.b_bytes);
-    uint64_t *tau_x = reinterpret_cast<uint64_t *>(&tail + 1);  // [256][2], NEPI == 16 only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int EPI0 = 1 + NMMA;  // first filter warp
@@ -274,7 +273,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tail.eb.acc_full[i], 1);
-            ptx::mbar_init(&tail.eb.acc_empty[i], 8);
+            ptx::mbar_init(&tail.eb.acc_empty[i], TC_EPI_WARPS);
         }
         ptx::mbar_init(&tail.eb.t0_ready, 1);
         ptx::fence_barrier_init();
@@ -396,7 +395,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         }
     } else {
         // ===================== epilogue: threshold filter =====================
-        epilogue_warps<GCAP, I8, NEPI>(args, warp - EPI0, warp & 3, lane, &tail.eb, tau_x);
+        epilogue_warps<GCAP, I8, EARLY>(args, warp - EPI0, warp & 3, lane, &tail.eb);
     }
 
     ptx::tc_fence_before_sync();
@@ -415,10 +414,11 @@ struct RerankArgs {
     const int *row_ids;    // second pass: absolute query index of every row instead
     const int *q_perm;     // locality order: absolute query index of every row; the query's vector
                            // is then row (q - q_begin) of `queries`
-    const int *base_perm;  // locality order: candidate position -> base row (null: identity)
+    const int *base_perm;  // locality order: candidate position -> base row (null: identity);
+                           // applied while the candidates are gathered
     int out_q_begin;       // output row = q - out_q_begin
     int n_rows, nb, d, k, kcap, self_join;
-    int nlists, gcap, npar;  // candidate lists per row = base splits x npar, capacity of one
+    int nlists, gcap;        // candidate lists per row (base splits), capacity of one
     int tail_row0, ns_tail;  // rows >= tail_row0 own ns_tail splits (knn_tc_common.cuh list_slot)
     const key64_t *cand;
     const int *cand_cnt;
@@ -448,9 +448,8 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
     const int ql = a.q_perm ? q - a.q_begin : r;  // row of `queries` / `qnorm64`
 
     // the row's threshold: the largest over its lists (each is a statement about the whole row)
-    const int my_splits = r < a.tail_row0 ? a.nlists : a.ns_tail;
-    const size_t slot0 = list_slot(r, 0, a.tail_row0, a.nlists, a.ns_tail) * a.npar;
-    const int my_lists = my_splits * a.npar;
+    const int my_lists = r < a.tail_row0 ? a.nlists : a.ns_tail;
+    const size_t slot0 = list_slot(r, 0, a.tail_row0, a.nlists, a.ns_tail);
     float tau = __int_as_float(0xff800000);
     for (int s = 0; s < my_lists; ++s) tau = fmaxf(tau, a.cand_tau[slot0 + s]);
     // candidates scoring below it cannot be among the row's best L: drop them unseen
@@ -464,10 +463,15 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         const key64_t *l = a.cand + (slot0 + s) * a.gcap;
         for (int i0 = 0; i0 < c; i0 += 32) {
             const int i = i0 + lane;
-            const key64_t kv = i < c ? __ldcg(l + i) : 0;
+            key64_t kv = i < c ? __ldcg(l + i) : 0;
             const bool keep = i < c && (uint32_t)(kv >> 32) <= hi_max;
             const unsigned kb = __ballot_sync(0xffffffffu, keep);
-            if (keep) keys[n + __popc(kb & lt_mask)] = kv;
+            if (keep) {
+                // locality order: the position in the permuted base operand -> the base row
+                if (a.base_perm)
+                    kv = (kv & 0xFFFFFFFF00000000ull) | (uint32_t)a.base_perm[(uint32_t)kv];
+                keys[n + __popc(kb & lt_mask)] = kv;
+            }
             n += __popc(kb);
         }
     }
@@ -492,8 +496,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
         // debug: the bound must dominate the real error of every score the kernel produced
         float worst = 0.0f;
         for (int i = lane; i < n; i += 32) {
-            const uint32_t pos = key_pos(keys[i]);
-            const uint32_t id = a.base_perm ? (uint32_t)a.base_perm[pos] : pos;
+            const uint32_t id = key_pos(keys[i]);
             const float s_tc = -key_score(keys[i]);
             const float *brow = a.base + (size_t)id * a.d;
             double dot = 0.0;
@@ -511,8 +514,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
     // exact distances: the scalar sequence of get_real_dist, one candidate per lane; keys are
     // rebuilt on (distance, base row) so that ties order by the caller's row numbers
     for (int i = lane; i < n; i += 32) {
-        const uint32_t pos = key_pos(keys[i]);
-        const uint32_t id = a.base_perm ? (uint32_t)a.base_perm[pos] : pos;
+        const uint32_t id = key_pos(keys[i]);
         const float *brow = a.base + (size_t)id * a.d;
         float acc = 0.0f;
         if ((a.d & 3) == 0) {
@@ -693,18 +695,17 @@ int pick_gcap(int L) {
     return L <= 96 ? 256 : 512;
 }
 
-size_t tc_smem_bytes(const TcPlan &p, int nepi) {
-    return 1024 + (size_t)p.a_bytes + (size_t)TC_NSTAGE * p.b_bytes + sizeof(TcSmemTail) +
-           (nepi == 16 ? (size_t)TC_ROWS * 2 * sizeof(uint64_t) : 0);
+size_t tc_smem_bytes(const TcPlan &p) {
+    return 1024 + (size_t)p.a_bytes + (size_t)TC_NSTAGE * p.b_bytes + sizeof(TcSmemTail);
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // does the resident-A plan fit in shared memory for this operand width?
-bool resident_fits(int op_cols, int nepi) {
+bool resident_fits(int op_cols) {
     TcPlan p;
     if (!build_plan(op_cols, &p)) return false;
-    return tc_smem_bytes(p, nepi) <= 227 * 1024;
+    return tc_smem_bytes(p) <= 227 * 1024;
 }
 
 constexpr int P2_GCAP = 512, P2_MAX_LISTS = 4;
@@ -713,16 +714,16 @@ constexpr int P2_GCAP = 512, P2_MAX_LISTS = 4;
 struct TcGeom {
     int n_qtiles, nsplit, tiles_per_split;
     int q_tail0, ns_tail, tiles_per_split_tail;
-    size_t n_slots;  // (row, split) pairs; each holds npar lists
+    size_t n_slots;  // (row, split) pairs: candidate lists
 };
 
-void tc_geom(int n_rows, int n_btiles, int gcap, int npar, int num_sms, TcGeom *g) {
+void tc_geom(int n_rows, int n_btiles, int gcap, int num_sms, TcGeom *g) {
     g->n_qtiles = (n_rows + TC_ROWS - 1) / TC_ROWS;
     // Base splits: a work item is (query tile, base split).  A split costs a second candidate list
     // per row with its own warm-up (measured: 100k x 128 takes 5.0 / 6.7 / 8.6 ms with 1 / 2 / 4
     // splits although 4 splits fill the last round of the grid best), so the base is only split
     // when the query tiles alone cannot occupy every SM once.
-    const int max_lists = 2048 / (gcap * npar);
+    const int max_lists = 2048 / gcap;
     int nsplit = 1;
     while (g->n_qtiles * nsplit < num_sms && nsplit * 2 <= max_lists && nsplit < 4 &&
            n_btiles / (nsplit * 2) >= 16)
@@ -758,7 +759,7 @@ void tc_geom(int n_rows, int n_btiles, int gcap, int npar, int num_sms, TcGeom *
 // exceed $PQH_TC_SLICE_MB (2 GiB by default; a slice is a whole number of rounds of the
 // persistent grid), whatever n is.
 struct TcLayout {
-    int d16, d32, L, L_exact, gcap, npar, nepi, nmma, n_btiles;
+    int d16, d32, L, L_exact, gcap, nmma, n_btiles;
     bool streaming, order;
     int slice_rows, slice_qtiles;
     size_t scalars, xh_b, fold_b, fold_a, norm_b, norm_q, xq, cand, cnt, tau, fb_rows, order_ws;
@@ -776,15 +777,13 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     lo->L = pick_L(kcap, true);
     lo->L_exact = pick_L(kcap, false);
     lo->gcap = pick_gcap(lo->L);
-    lo->nepi = ev.nepi;
-    lo->streaming = ev.streaming || !resident_fits(lo->d16, lo->nepi);
+    lo->streaming = ev.streaming || !resident_fits(lo->d16);
     lo->nmma = lo->streaming ? 1 : ev.nmma;
-    lo->npar = lo->nepi / 8;
     lo->order = ev.order && nb >= 8192;
     lo->n_btiles = (nb + TC_BN - 1) / TC_BN;
     // row slice: as many whole rounds of the grid as the list budget allows
     {
-        const size_t per_row = (size_t)lo->gcap * lo->npar * sizeof(key64_t);
+        const size_t per_row = (size_t)lo->gcap * sizeof(key64_t);
         long long rows = (long long)((size_t)ev.slice_mb * 1024 * 1024 / per_row);
         const long long round = (long long)num_sms * TC_ROWS;
         rows = rows / round * round;
@@ -797,15 +796,15 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     size_t max_slots = 0;
     {
         TcGeom g;
-        tc_geom(lo->slice_rows, lo->n_btiles, lo->gcap, lo->npar, num_sms, &g);
+        tc_geom(lo->slice_rows, lo->n_btiles, lo->gcap, num_sms, &g);
         max_slots = g.n_slots;
         const int last = n_rows % lo->slice_rows;
         if (last) {
-            tc_geom(last, lo->n_btiles, lo->gcap, lo->npar, num_sms, &g);
+            tc_geom(last, lo->n_btiles, lo->gcap, num_sms, &g);
             if (g.n_slots > max_slots) max_slots = g.n_slots;
         }
     }
-    const size_t n_lists = max_slots * lo->npar;
+    const size_t n_lists = max_slots;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -842,24 +841,23 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     lo->total = off + 1024;
 }
 
-template <int GCAP, bool I8, int NEPI, int NMMA>
+template <int GCAP, bool I8, int NMMA, bool EARLY>
 cudaError_t launch_tc_one(const TcMaps &maps, const TcArgs &args, size_t smem, int grid,
                           cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<GCAP, I8, NEPI, NMMA>,
+    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<GCAP, I8, NMMA, EARLY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    knn_tc_kernel<GCAP, I8, NEPI, NMMA>
-        <<<grid, tc_threads(NEPI) + (NMMA - 1) * 32, smem, stream>>>(maps, args);
+    knn_tc_kernel<GCAP, I8, NMMA, EARLY><<<grid, tc_threads(NMMA), smem, stream>>>(maps, args);
     return cudaGetLastError();
 }
 template <int GCAP, bool I8>
-cudaError_t launch_tc_cfg(const TcMaps &maps, const TcArgs &args, size_t smem, int grid, int nepi,
-                          int nmma, cudaStream_t stream) {
-    if (nepi == 16)
-        return nmma == 2 ? launch_tc_one<GCAP, I8, 16, 2>(maps, args, smem, grid, stream)
-                         : launch_tc_one<GCAP, I8, 16, 1>(maps, args, smem, grid, stream);
-    return nmma == 2 ? launch_tc_one<GCAP, I8, 8, 2>(maps, args, smem, grid, stream)
-                     : launch_tc_one<GCAP, I8, 8, 1>(maps, args, smem, grid, stream);
+cudaError_t launch_tc_cfg(const TcMaps &maps, const TcArgs &args, size_t smem, int grid, int nmma,
+                          bool early, cudaStream_t stream) {
+    if (early)
+        return nmma == 2 ? launch_tc_one<GCAP, I8, 2, true>(maps, args, smem, grid, stream)
+                         : launch_tc_one<GCAP, I8, 1, true>(maps, args, smem, grid, stream);
+    return nmma == 2 ? launch_tc_one<GCAP, I8, 2, false>(maps, args, smem, grid, stream)
+                     : launch_tc_one<GCAP, I8, 1, false>(maps, args, smem, grid, stream);
 }
 
 }  // namespace
@@ -868,8 +866,8 @@ void tc_reload_env() {
     TcEnv e;
     e.i8 = env_int("PQH_TC_I8", 1) != 0;
     e.order = env_int("PQH_TC_ORDER", 1) != 0;
-    e.nepi = env_int("PQH_TC_EPI", 8) == 16 ? 16 : 8;
     e.nmma = env_int("PQH_TC_MMA", 1) == 2 ? 2 : 1;
+    e.early = env_int("PQH_TC_EARLY", 0) != 0;
     e.l_exact = env_int("PQH_TC_LEXACT", 0);
     e.l_inexact = env_int("PQH_TC_LINEXACT", 0);
     e.gcap = env_int("PQH_TC_GCAP", 0);
@@ -969,7 +967,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     // ---- base operand, integer flavour: tried first, kept only if every value qualifies ----
     bool used_i8 = false;
     const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode == 0 || debug_mode == 1) &&
-                             resident_fits(lo.d32 / 2, lo.nepi);
+                             resident_fits(lo.d32 / 2);
     if (i8_possible) {
         prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(
             d_base, nb, d, lo.d32, reinterpret_cast<uint8_t *>(xh_b), norm_b,
@@ -1013,7 +1011,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     // ---- one pass = tensor-core kernel + re-rank over a set of query rows ----
     struct Pass {
         TcGeom g;
-        int L_exact, L_inexact, gcap, npar, nepi, nmma;
+        int L_exact, L_inexact, gcap, nmma;
         bool streaming;
         const void *a_op;        // query operand: row (q_op_begin + r) is query row r
         uint64_t a_rows;         // rows of that operand
@@ -1077,22 +1075,18 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         cudaError_t pe;
         if (p.ev3) cudaEventRecord(p.ev3[0], stream);
         if (p.streaming) {
-            if ((pe = launch_tcs(&maps, &args, p.gcap, lo.d16, n_items, num_sms, p.nepi, stream)) !=
+            if ((pe = launch_tcs(&maps, &args, p.gcap, lo.d16, n_items, num_sms, stream)) !=
                 cudaSuccess)
                 return pe;
         } else {
             const int grid = n_items < num_sms ? n_items : num_sms;
-            const size_t smem = tc_smem_bytes(args.plan, p.nepi);
+            const size_t smem = tc_smem_bytes(args.plan);
             if (p.i8)
-                pe = p.gcap == 256 ? launch_tc_cfg<256, true>(maps, args, smem, grid, p.nepi,
-                                                               p.nmma, stream)
-                                   : launch_tc_cfg<512, true>(maps, args, smem, grid, p.nepi,
-                                                               p.nmma, stream);
+                pe = p.gcap == 256 ? launch_tc_cfg<256, true>(maps, args, smem, grid, p.nmma, ev.early != 0, stream)
+                                   : launch_tc_cfg<512, true>(maps, args, smem, grid, p.nmma, ev.early != 0, stream);
             else
-                pe = p.gcap == 256 ? launch_tc_cfg<256, false>(maps, args, smem, grid, p.nepi,
-                                                                p.nmma, stream)
-                                   : launch_tc_cfg<512, false>(maps, args, smem, grid, p.nepi,
-                                                                p.nmma, stream);
+                pe = p.gcap == 256 ? launch_tc_cfg<256, false>(maps, args, smem, grid, p.nmma, ev.early != 0, stream)
+                                   : launch_tc_cfg<512, false>(maps, args, smem, grid, p.nmma, ev.early != 0, stream);
             if (pe != cudaSuccess) return pe;
         }
         ++*launches;
@@ -1114,7 +1108,6 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         ra.kcap = kcap;
         ra.self_join = self_join;
         ra.nlists = p.g.nsplit;
-        ra.npar = p.npar;
         ra.tail_row0 = p.g.q_tail0 * TC_ROWS;
         ra.ns_tail = p.g.ns_tail;
         ra.gcap = p.gcap;
@@ -1132,7 +1125,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         ra.fb_rows = p.fb_rows;
         ra.fb_count = p.fb_count;
         const int splits = p.g.nsplit > p.g.ns_tail ? p.g.nsplit : p.g.ns_tail;
-        const int nmax = p.gcap * splits * p.npar;
+        const int nmax = p.gcap * splits;
         const int rgrid = (p.n_rows + RR_WARPS - 1) / RR_WARPS;
         const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
 #define LAUNCH_RR(N)                                                                             \
@@ -1163,7 +1156,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         const float *q_slice = q_mat + (size_t)(q_src0 + si * lo.slice_rows) * d;
         double *qn_slice = (self_join ? norm_b + s_begin : norm_q + (size_t)si * lo.slice_rows);
         Pass p1;
-        tc_geom(rows, lo.n_btiles, lo.gcap, lo.npar, num_sms, &p1.g);
+        tc_geom(rows, lo.n_btiles, lo.gcap, num_sms, &p1.g);
         if (lo.order) {
             if ((e = launch_order_queries(self_join ? nullptr : q_slice, s_begin, rows, nb, d,
                                           self_join, p1.g.n_qtiles, lo.slice_rows,
@@ -1196,8 +1189,6 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         p1.L_exact = lo.L_exact;
         p1.L_inexact = lo.L;
         p1.gcap = lo.gcap;
-        p1.npar = lo.npar;
-        p1.nepi = lo.nepi;
         p1.nmma = lo.nmma;
         p1.streaming = lo.streaming;
         p1.i8 = used_i8;
@@ -1257,13 +1248,13 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             int *self2 = reinterpret_cast<int *>(w + lo.p2_self);
             const float *src = self_join ? d_base : d_queries;
             const int src_row0 = self_join ? 0 : q_row0;
-            const bool stream2 = ev.streaming || !resident_fits(lo.d16, 8);
+            const bool stream2 = lo.streaming;
             for (unsigned done = 0; done < n_fb1; done += (unsigned)lo.p2_rows) {
                 const int n2 = (int)(n_fb1 - done < (unsigned)lo.p2_rows ? n_fb1 - done
                                                                           : (unsigned)lo.p2_rows);
                 const int *ids = fb_rows + done;
                 Pass p2;
-                tc_geom(n2, lo.n_btiles, P2_GCAP, 1, num_sms, &p2.g);
+                tc_geom(n2, lo.n_btiles, P2_GCAP, num_sms, &p2.g);
                 if (p2.g.nsplit > P2_MAX_LISTS || p2.g.ns_tail > P2_MAX_LISTS)
                     return cudaErrorInvalidValue;
                 gather_rows_kernel<<<(n2 + 7) / 8, 256, 0, stream>>>(src, src_row0, ids, n2, d, q2);
@@ -1282,8 +1273,6 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                     return e;
                 p2.L_exact = p2.L_inexact = L2;
                 p2.gcap = P2_GCAP;
-                p2.npar = 1;
-                p2.nepi = 8;
                 p2.nmma = 1;
                 p2.streaming = stream2;
                 p2.a_op = xh2;
@@ -1329,8 +1318,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         if (debug_mode)
             fprintf(stderr,
                     "tc dbg: mma threads: barrier waits %.4g cyc of %.4g cyc (sums over CTAs and "
-                    "issuers) | pass-1 failures %u | epi %d mma %d order %d slices %d\n",
-                    (double)hsc.dbg[0], (double)hsc.dbg[1], n_fb1, lo.nepi, lo.nmma,
+                    "issuers) | slow (warp, tile) pairs %.4g | pass-1 failures %u | mma %d order %d "
+                    "slices %d\n",
+                    (double)hsc.dbg[0], (double)hsc.dbg[1], (double)hsc.dbg[2], n_fb1, lo.nmma,
                     (int)lo.order, n_slices);
         cudaEventElapsedTime(&times->ms_prep, evs[0], evs[1]);
         times->ms_gemm = times->ms_rerank = 0.f;

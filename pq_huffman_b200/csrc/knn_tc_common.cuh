@@ -23,13 +23,9 @@ constexpr int TC_BN = 128;      // base rows per tile (UMMA N)
 constexpr int TC_NSTAGE = 4;    // B-tile ring
 constexpr int TC_MAXSEG = 6;
 constexpr int FOLD_COLS = 16;
-// warp 0 TMA, warp 1 MMA, then NEPI filter warps: 8 (each warp filters every tile of its 32 rows)
-// or 16 (two warps per 32 rows, one per accumulator stage; see epilogue_warps)
-__host__ __device__ constexpr int tc_threads(int nepi) { return (2 + nepi) * 32; }
-// registers per thread of a one-CTA-per-SM kernel: the 64K file over the warps, in units of 8
-__host__ __device__ constexpr int tc_max_regs(int threads) {
-    return 65536 / threads / 8 * 8 > 255 ? 255 : 65536 / threads / 8 * 8;
-}
+constexpr int TC_EPI_WARPS = 8;  // filter warps: each owns 32 query rows (a TMEM lane quadrant)
+// warp 0 TMA, then `nmma` MMA issuers, then the filter warps
+__host__ __device__ constexpr int tc_threads(int nmma) { return (1 + nmma + TC_EPI_WARPS) * 32; }
 
 constexpr int I8_FOLD_FULL = 30;         // fold columns with A-side constant 255 (the last two: 1)
 constexpr int I8_FOLD_UNIT = 255 * 128;  // what one full column can subtract
@@ -60,7 +56,8 @@ struct PrepScalars {
     uint32_t i8_reject;    // integer path: bit 0 = a value is not an integer in [0, 255],
                            // bit 1 = |y|^2 beyond the capacity of the fold columns
     unsigned long long cand_total[32];  // candidates re-ranked (spread to avoid contention)
-    unsigned long long dbg[8];          // PQH_TC_DEBUG: MMA-thread cycle counters
+    unsigned long long dbg[8];          // [0],[1] PQH_TC_DEBUG: MMA-thread cycle counters;
+                                        // [2] (warp, tile) pairs that took the slow path
 };
 
 struct TcArgs {
@@ -123,7 +120,7 @@ __device__ __forceinline__ ItemInfo decode_item(const TcArgs &a, int item) {
     if (it.t_hi > a.n_btiles) it.t_hi = a.n_btiles;
     return it;
 }
-// candidate-list slot of (query row r of this launch, base split sp); a slot holds `npar` lists
+// candidate-list slot of (query row r of this launch, base split sp)
 __host__ __device__ __forceinline__ size_t list_slot(int r, int sp, int tail_row0, int nsplit,
                                                       int ns_tail) {
     return r < tail_row0 ? (size_t)r * nsplit + sp
@@ -344,135 +341,112 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
     cnt += p ? 1 : 0;
 }
 
-// maxima of the two groups of 8 columns held in v[0..16)
-template <bool I8>
-__device__ __forceinline__ void group_maxima16(const uint32_t (&v)[16],
-                                               typename Score<I8>::T *gm) {
-    typedef Score<I8> S;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const uint32_t *b = &v[q * 8];
-        typename S::T m = S::max3(S::from_bits(b[0]), S::from_bits(b[1]), S::from_bits(b[2]));
-        m = S::max3(m, S::from_bits(b[3]), S::from_bits(b[4]));
-        m = S::max3(m, S::from_bits(b[5]), S::from_bits(b[6]));
-        gm[q] = S::max2(m, S::from_bits(b[7]));
-    }
-}
-
 // Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
 // it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
 //
 // Hot path (kept small and contiguous -- it must live in the instruction cache): copy the
-// 32 x 128 slice to registers, reduce it to 16 group maxima (groups of 8 columns) with 3-input
-// max, compare with the row's threshold tau and OR the 16-bit result over the warp.  No bit set
-// (the common case): release the accumulator stage and return.  WIDE (8 filter warps, 168
-// registers): two 64-column tcgen05.ld in flight together; otherwise (16 filter warps: 20 warps
-// per CTA leave 96 registers per thread) eight 16-column loads, two in flight, the maxima of
-// one computed while the next is on its way.
-// Slow path (one small loop, no unrolled copies): for every flagged group re-read its 8 columns
-// from TMEM by address and append the scores above tau to the row's candidate list with
-// predicated stores (no divergent branches); then release the stage, then -- rarely -- shrink a
-// list that reached its hard capacity.
-template <int GCAP, bool I8, bool WIDE, class Release>
+// 32 x 128 slice to registers with two 64-column tcgen05.ld in flight together, reduce it to
+// 16 group maxima (groups of 8 columns) with 3-input max -- level by level, so that sixteen
+// independent operations are in flight at any time -- compare with the row's threshold tau and
+// OR the 16-bit result over the warp.  No bit set (the common case): done.
+// Slow path, two flavours:
+//   EARLY  the accumulator stage is released as soon as the copy has landed (the tile then
+//          lives in registers and the tensor cores never wait for the filtering); flagged groups
+//          (warp-uniform test) are appended straight from the registers;
+//   !EARLY flagged groups are re-read from TMEM by address in one small loop (no unrolled
+//          copies) and the stage is released after that -- before the scan when at most two
+//          groups are flagged.
+// Either way scores above tau go to the row's candidate list with predicated stores (no
+// divergent branches), and a list that reached its hard capacity is shrunk (rare).
+template <int GCAP, bool I8, bool EARLY, class Release>
 __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
                                             int self, int L, int lane, int debug_mode,
                                             typename Score<I8>::T &tau, int &cnt, key64_t *list,
-                                            Release release) {
+                                            unsigned &slow_tiles, Release release) {
     typedef Score<I8> S;
     typedef typename S::T T;
     constexpr int NG = TC_BN / 8;  // groups of 8 columns
-    unsigned groups = 0;
-    {
-        T gm[NG];
-        if constexpr (WIDE) {
-            uint32_t ra[64], rb[64];
-            ptx::tmem_ld_32x32b_x64(tbase, ra);
-            ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
-            ptx::tmem_wait_ld();
+    uint32_t ra[64], rb[64];
+    ptx::tmem_ld_32x32b_x64(tbase, ra);
+    ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+    ptx::tmem_wait_ld();
+    if (EARLY) release();
+#define PQH_V(q, j) S::from_bits(((q) < 8) ? ra[(q) * 8 + (j)] : rb[((q) - 8) * 8 + (j)])
+    T gm[NG];
 #pragma unroll
-            for (int q = 0; q < NG; ++q) {
-                const uint32_t *b = (q < 8) ? &ra[q * 8] : &rb[(q - 8) * 8];
-                T m = S::max3(S::from_bits(b[0]), S::from_bits(b[1]), S::from_bits(b[2]));
-                m = S::max3(m, S::from_bits(b[3]), S::from_bits(b[4]));
-                m = S::max3(m, S::from_bits(b[5]), S::from_bits(b[6]));
-                gm[q] = S::max2(m, S::from_bits(b[7]));
-            }
-        } else {
-            // two 16-column loads in flight; the wait is not selective (it completes every load
-            // issued so far), so each round waits for the older one and reissues its buffer
-            uint32_t r0[16], r1[16];
-            ptx::tmem_ld_32x32b_x16(tbase, r0);
-            ptx::tmem_ld_32x32b_x16(tbase + 16, r1);
+    for (int q = 0; q < NG; ++q) gm[q] = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                ptx::tmem_wait_ld_16(r0);
-                group_maxima16<I8>(r0, gm + 2 * c);
-                if (c + 2 < 8) ptx::tmem_ld_32x32b_x16(tbase + 16 * (c + 2), r0);
-                ptx::tmem_wait_ld_16(r1);
-                group_maxima16<I8>(r1, gm + 2 * c + 2);
-                if (c + 3 < 8) ptx::tmem_ld_32x32b_x16(tbase + 16 * (c + 3), r1);
-            }
-        }
-        T rm = gm[0];
+    for (int q = 0; q < NG; ++q) gm[q] = S::max3(gm[q], PQH_V(q, 3), PQH_V(q, 4));
 #pragma unroll
-        for (int q = 1; q + 1 < NG; q += 2) rm = S::max3(rm, gm[q], gm[q + 1]);
-        rm = S::max2(rm, gm[NG - 1]);
-        // common case: no row of the warp has anything above its threshold -> one vote, done
-        if (__any_sync(0xffffffffu, rm > tau)) {
-            unsigned gmask = 0;
+    for (int q = 0; q < NG; ++q) gm[q] = S::max3(gm[q], PQH_V(q, 5), PQH_V(q, 6));
 #pragma unroll
-            for (int q = 0; q < NG; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
-            groups = __reduce_or_sync(0xffffffffu, gmask);
-        }
-    }
-    if (groups == 0 || debug_mode == 2) {
-        release();
+    for (int q = 0; q < NG; ++q) gm[q] = S::max2(gm[q], PQH_V(q, 7));
+    const T r0 = S::max3(gm[0], gm[1], gm[2]), r1 = S::max3(gm[3], gm[4], gm[5]);
+    const T r2 = S::max3(gm[6], gm[7], gm[8]), r3 = S::max3(gm[9], gm[10], gm[11]);
+    const T r4 = S::max3(gm[12], gm[13], gm[14]);
+    const T rm = S::max3(S::max3(r0, r1, r2), S::max3(r3, r4, gm[15]), S::lowest());
+    // common case: no row of the warp has anything above its threshold -> one vote, done
+    if (!__any_sync(0xffffffffu, rm > tau) || debug_mode == 2) {
+        if (!EARLY) release();
         return;
     }
+    unsigned gmask = 0;
+#pragma unroll
+    for (int q = 0; q < NG; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
+    unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
+    ++slow_tiles;
+    // ragged last tile / the row's own column: only "special" tiles carry a real limit
     const int id_lim = special ? ib_hi : 0x7fffffff;
-    // the id checks (ragged last tile, the row's own column) are only compiled into the copy of
-    // the scan that "special" tiles take; the choice is made warp-uniform
-    const bool any_special = __any_sync(0xffffffffu, special);
-    auto scan8 = [&](const uint32_t(&v8)[8], int q) {
-        const int col0 = col_base + q * 8;
-        if (any_special) {
+    if constexpr (EARLY) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            if (groups & (1u << q)) {  // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int id = col_base + q * 8 + j;
+                    const uint32_t bits = (q < 8) ? ra[q * 8 + j] : rb[(q - 8) * 8 + j];
+                    const bool p = (S::from_bits(bits) > tau) & (id < id_lim) & (id != self);
+                    append_if<I8>(p, list, cnt, bits, id);
+                }
+            }
+        }
+    } else {
+        auto scan8 = [&](const uint32_t(&v8)[8], int q) {
+            const int col0 = col_base + q * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int id = col0 + j;
                 const bool p = (S::from_bits(v8[j]) > tau) & (id < id_lim) & (id != self);
                 append_if<I8>(p, list, cnt, v8[j], id);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                append_if<I8>(S::from_bits(v8[j]) > tau, list, cnt, v8[j], col0 + j);
-        }
-    };
-    const int q1 = __ffs(groups) - 1;
-    const unsigned rest = groups & (groups - 1);
-    if ((rest & (rest - 1)) == 0) {
-        // one or two flagged groups (the usual slow tile): fetch them, give the accumulator
-        // stage back, and only then scan -- the scan is off the tensor cores' critical path
-        const int q2 = rest ? __ffs(rest) - 1 : q1;
-        uint32_t va[8], vb[8];
-        ptx::tmem_ld_32x32b_x8(tbase + q1 * 8, va);
-        ptx::tmem_ld_32x32b_x8(tbase + q2 * 8, vb);
-        ptx::tmem_wait_ld();
-        release();
-        scan8(va, q1);
-        if (rest) scan8(vb, q2);
-    } else {
-#pragma unroll 1
-        do {
-            const int q = __ffs(groups) - 1;
-            groups &= groups - 1;
-            uint32_t v8[8];
-            ptx::tmem_ld_32x32b_x8(tbase + q * 8, v8);
+        };
+        const int q1 = __ffs(groups) - 1;
+        const unsigned rest = groups & (groups - 1);
+        if ((rest & (rest - 1)) == 0) {
+            // one or two flagged groups (the usual slow tile): fetch them, give the accumulator
+            // stage back, and only then scan -- the scan is off the tensor cores' critical path
+            const int q2 = rest ? __ffs(rest) - 1 : q1;
+            uint32_t va[8], vb[8];
+            ptx::tmem_ld_32x32b_x8(tbase + q1 * 8, va);
+            ptx::tmem_ld_32x32b_x8(tbase + q2 * 8, vb);
             ptx::tmem_wait_ld();
-            scan8(v8, q);
-        } while (groups != 0);
-        release();
+            release();
+            scan8(va, q1);
+            if (rest) scan8(vb, q2);
+        } else {
+#pragma unroll 1
+            do {
+                const int q = __ffs(groups) - 1;
+                groups &= groups - 1;
+                uint32_t v8[8];
+                ptx::tmem_ld_32x32b_x8(tbase + q * 8, v8);
+                ptx::tmem_wait_ld();
+                scan8(v8, q);
+            } while (groups != 0);
+            release();
+        }
     }
+#undef PQH_V
     if (cnt > GCAP) __trap();  // list overflow would silently corrupt a neighbouring row's list
     // hard capacity: a tile can append up to TC_BN entries before this check runs again
     shrink_flagged<GCAP, I8, false>(__ballot_sync(0xffffffffu, cnt > GCAP - TC_BN), L, lane, tau,
@@ -499,30 +473,6 @@ __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32
     }
 }
 
-// Thresholds exchanged between the two warps that share 32 query rows when there are 16 filter
-// warps: (work item << 32) | bits of tau, one 8-byte word per (row, warp of the pair).  A
-// threshold is a statement about the ROW ("at least L candidates of this row score >= tau"),
-// so either warp may adopt the other's; the item tag keeps a warp that is already in the next
-// work item from reading a threshold of the previous one.
-template <bool I8>
-__device__ __forceinline__ uint64_t pack_tau(int item, typename Score<I8>::T tau) {
-    uint32_t b;
-    if constexpr (I8) b = (uint32_t)tau;
-    else b = __float_as_uint(tau);
-    return ((uint64_t)(uint32_t)item << 32) | b;
-}
-
-// The filter warps of one CTA: filter warp e (0 .. NEPI-1) owns TMEM lane quadrant `quad` of
-// query tile g = (e >> 2) & 1, i.e. 32 query rows, one per lane.
-//   NEPI == 8:  the warp filters every base tile of the sweep for its rows.
-//   NEPI == 16: warps e and e + 8 share the same 32 rows; warp e takes the tiles that land in
-//               accumulator stage 0 (even steps), warp e + 8 those of stage 1.  Each keeps its
-//               own candidate list and count (list index 2 * slot + stage) and they exchange
-//               thresholds through shared memory (tau_x).  Twice the warps per scheduler hide
-//               the tensor-memory and barrier latencies of the hot path, and a warp has two tile
-//               times for a slow tile.
-// Steps are numbered over the whole life of the CTA (gstep): stage = step & 1, barrier phase =
-// (step >> 1) & 1.
 // Barriers and hand-over words the filter warps use, in the shared-memory tail of both kernels.
 struct EpiBars {
     uint64_t acc_full[2], acc_empty[2];
@@ -531,22 +481,25 @@ struct EpiBars {
     int item_t0[2];     // first base tile of the current / next work item (set by the producer)
 };
 
-template <int GCAP, bool I8, int NEPI>
+// The filter warps of one CTA: filter warp e (0 .. 7) owns TMEM lane quadrant `quad` (= its
+// warp index & 3: the quadrant the hardware lets it read; four consecutive warps cover the
+// four quadrants whatever the index of the first filter warp is) of query tile g = e >> 2,
+// i.e. 32 query rows, one per lane, and filters every base tile of the sweep for them.
+// Steps are numbered over the whole life of the CTA (gstep): accumulator stage = step & 1,
+// barrier phase = (step >> 1) & 1.
+template <int GCAP, bool I8, bool EARLY>
 __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int quad, int lane,
-                                               EpiBars *eb, uint64_t *tau_x) {
+                                               EpiBars *eb) {
     typedef Score<I8> S;
     typedef typename S::T T;
-    constexpr int NPAR = NEPI / 8;
-    const int g = (e >> 2) & 1;
-    const int par = e >> 3;  // 0 when NEPI == 8
-    // quad = warp index & 3: the TMEM lane quadrant this warp may read; four consecutive warps
-    // cover the four quadrants whatever the index of the first filter warp is
+    const int g = e >> 2;
     const int row_in_cta = g * 128 + quad * 32 + lane;
     const uint32_t tmem_row = eb->tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 128);
     const int L = args.sc->inexact ? args.L_inexact : args.L_exact;
     const int n_items = total_items(args);
     uint32_t gstep = 0;
     int it_par = 0;
+    unsigned slow_tiles = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ItemInfo it = decode_item(args, item);
         const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
@@ -556,41 +509,25 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
         if (valid && args.self_join)
             self = args.q_self ? args.q_self[r] : (args.row_ids ? args.row_ids[r] : args.q_begin + r);
         const size_t slot =
-            valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail) * NPAR + par
-                  : 0;
+            valid ? list_slot(r, sp, args.q_tail0 * TC_ROWS, args.nsplit, args.ns_tail) : 0;
         key64_t *list = args.cand + slot * GCAP;
         T tau = valid ? S::lowest() : S::highest();
-        T tau_pub = tau;
         int cnt = 0;
         long long b_hi = (long long)t_hi * TC_BN;
         if (b_hi > args.nb) b_hi = args.nb;
         const int ib_hi = (int)b_hi;
-        if (NPAR == 2) tau_x[row_in_cta * 2 + par] = pack_tau<I8>(item, tau);
 
         const int nst = t_hi - t_lo;
         int t0 = 0;
-        bool first = true;
-        for (int i = (NPAR == 2) ? (int)((par ^ gstep) & 1u) : 0; i < nst; i += NPAR) {
+        for (int i = 0; i < nst; ++i) {
             const uint32_t s = gstep + (uint32_t)i;
             const int as = (int)(s & 1u);
             const uint32_t acc_ph = (s >> 1) & 1u;
             wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
             ptx::tc_fence_after_sync();
-            if (first) {
+            if (i == 0) {
                 ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
                 t0 = *reinterpret_cast<volatile int *>(&eb->item_t0[it_par]);
-                first = false;
-            }
-            if (NPAR == 2) {
-                // adopt the partner's threshold if it belongs to this work item and is higher
-                const uint64_t px = *reinterpret_cast<volatile uint64_t *>(
-                    &tau_x[row_in_cta * 2 + (par ^ 1)]);
-                if ((int)(px >> 32) == item) {
-                    T pt;
-                    if constexpr (I8) pt = (int)(uint32_t)px;
-                    else pt = __uint_as_float((uint32_t)px);
-                    tau = S::max2(tau, pt);
-                }
             }
             const int t = item_tile(i, t0, t_lo, t_hi);
             const uint32_t tbase = tmem_row + (uint32_t)(as * 256);
@@ -604,15 +541,10 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
                 if (lane == 0) ptx::mbar_arrive(&eb->acc_empty[as]);
             };
             if (args.debug_mode != 1)
-                filter_tile<GCAP, I8, NEPI == 8>(tbase, tile0, special, ib_hi, self, L, lane,
-                                                 args.debug_mode, tau, cnt, list, release);
+                filter_tile<GCAP, I8, EARLY>(tbase, tile0, special, ib_hi, self, L, lane,
+                                             args.debug_mode, tau, cnt, list, slow_tiles, release);
             else
                 release();
-            if (NPAR == 2 && tau != tau_pub) {
-                *reinterpret_cast<volatile uint64_t *>(&tau_x[row_in_cta * 2 + par]) =
-                    pack_tau<I8>(item, tau);
-                tau_pub = tau;
-            }
         }
         gstep += (uint32_t)nst;
         it_par ^= 1;
@@ -621,6 +553,8 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
             args.cand_tau[slot] = S::as_float(tau);
         }
     }
+    if (lane == 0 && slow_tiles)
+        atomicAdd(const_cast<unsigned long long *>(&args.sc->dbg[2]), (unsigned long long)slow_tiles);
 }
 
 }  // namespace

@@ -2,7 +2,7 @@
 // does not fit in shared memory (GIST-shaped d = 960, anything above ~144).
 //
 // Same geometry and epilogue as knn_tc_kernel (256 query rows per CTA as two M=128 accumulator
-// tiles, base tiles of 128 rows, two accumulator stages, 8 or 16 filter warps), but BOTH operands
+// tiles, base tiles of 128 rows, two accumulator stages, eight filter warps), but BOTH operands
 // are streamed through one ring of K-blocks: a stage holds the [256 x 64] slice of the query
 // tile and the [128 x 64] slice of the base tile for one K-block (48 KB), the MMA thread
 // accumulates over all K-blocks of a tile before committing the accumulator.  With d this large
@@ -70,14 +70,13 @@ struct KBlocks {
     }
 };
 
-template <int GCAP, int NEPI>
-__global__ void __launch_bounds__(tc_threads(NEPI), 1) __maxnreg__(tc_max_regs(tc_threads(NEPI)))
+template <int GCAP>
+__global__ void __launch_bounds__(tc_threads(1), 1)
 knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     TsSmemTail &tail = *reinterpret_cast<TsSmemTail *>(smem + TS_NSTAGE * TS_STAGE_BYTES);
-    uint64_t *tau_x = reinterpret_cast<uint64_t *>(&tail + 1);  // [256][2], NEPI == 16 only
     const KBlocks kb(d16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,7 +96,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tail.eb.acc_full[i], 1);
-            ptx::mbar_init(&tail.eb.acc_empty[i], 8);
+            ptx::mbar_init(&tail.eb.acc_empty[i], TC_EPI_WARPS);
         }
         ptx::mbar_init(&tail.eb.t0_ready, 1);
         ptx::fence_barrier_init();
@@ -197,7 +196,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
         }
     } else {
         // ===================== epilogue: threshold filter (as knn_tc_kernel) =================
-        epilogue_warps<GCAP, false, NEPI>(args, warp - 2, warp & 3, lane, &tail.eb, tau_x);
+        epilogue_warps<GCAP, false, false>(args, warp - 2, warp & 3, lane, &tail.eb);
     }
 
     ptx::tc_fence_before_sync();
@@ -205,30 +204,26 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
-template <int GCAP, int NEPI>
+template <int GCAP>
 cudaError_t launch_tcs_one(const TcMaps &maps, const TcArgs &args, int d16, int grid,
                            cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t)TS_NSTAGE * TS_STAGE_BYTES + sizeof(TsSmemTail) +
-                        (NEPI == 16 ? (size_t)TC_ROWS * 2 * sizeof(uint64_t) : 0);
-    cudaError_t e = cudaFuncSetAttribute(knn_tcs_kernel<GCAP, NEPI>,
+    const size_t smem = 1024 + (size_t)TS_NSTAGE * TS_STAGE_BYTES + sizeof(TsSmemTail);
+    cudaError_t e = cudaFuncSetAttribute(knn_tcs_kernel<GCAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    knn_tcs_kernel<GCAP, NEPI><<<grid, tc_threads(NEPI), smem, stream>>>(maps, args, d16);
+    knn_tcs_kernel<GCAP><<<grid, tc_threads(1), smem, stream>>>(maps, args, d16);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_tcs(const void *maps_v, const void *args_v, int gcap, int d16, int n_items,
-                       int num_sms, int nepi, cudaStream_t stream) {
+                       int num_sms, cudaStream_t stream) {
     const TcMaps &maps = *static_cast<const TcMaps *>(maps_v);
     const TcArgs &args = *static_cast<const TcArgs *>(args_v);
     const int grid = n_items < num_sms ? n_items : num_sms;
-    if (nepi == 16)
-        return gcap == 256 ? launch_tcs_one<256, 16>(maps, args, d16, grid, stream)
-                           : launch_tcs_one<512, 16>(maps, args, d16, grid, stream);
-    return gcap == 256 ? launch_tcs_one<256, 8>(maps, args, d16, grid, stream)
-                       : launch_tcs_one<512, 8>(maps, args, d16, grid, stream);
+    return gcap == 256 ? launch_tcs_one<256>(maps, args, d16, grid, stream)
+                       : launch_tcs_one<512>(maps, args, d16, grid, stream);
 }
 
 }  // namespace pqh

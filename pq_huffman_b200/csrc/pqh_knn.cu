@@ -28,6 +28,7 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -100,6 +101,8 @@ bool load_nccl(std::string *why) {
     g_nccl = a;
     return true;
 }
+
+constexpr int MAX_DEVS = 16;
 
 // ---- device buffers ---------------------------------------------------------------------------
 struct DevBuf {
@@ -174,11 +177,29 @@ struct DeviceCtx {
     int ds_n = 0, ds_d = 0;
 };
 
+// Device-side merge state of the partitioned mode: the per-vector heaps the reference keeps in
+// its temp file (fast_nn_temp_file.h:11-14: k x {uint32 index, float dist} per vector), resident
+// on device slot 0.  Merges are applied in ticket (= block) order on one stream of that device,
+// so the heaps go through exactly the states the reference's serial loop produces.
+struct MergeState {
+    long long n = 0;
+    int k = 0;
+    DevBuf heaps, work, out_ids, out_dists;  // device slot 0
+    DevBuf peer_ids, peer_assign, peer_dis;  // landing buffers for blocks searched elsewhere
+    cudaStream_t stream = nullptr;           // on device slot 0
+    cudaEvent_t searched[MAX_DEVS] = {};     // per slot: block search finished
+    cudaEvent_t consumed[MAX_DEVS] = {};     // per slot: its result buffers were read by the merge
+    std::mutex mu;
+    std::condition_variable cv;
+    long long next_ticket = 0;
+};
+
 struct Context {
     std::vector<DeviceCtx> devs;
     bool nccl = false;  // communicators over all devices exist
     pqh_knn_stats_t stats;
     std::vector<int> failed;  // rows of the last search the first tensor-core pass left open
+    MergeState merge;
 };
 
 std::mutex g_mu;
@@ -186,7 +207,6 @@ std::mutex g_mu;
 // that touches one device's buffers is serialised (lock order: g_mu, then g_dev_mu[slot]).
 // Entry points hold a shared_ptr to the context for their whole duration, so pqh_knn_init /
 // pqh_knn_shutdown from another thread cannot free it under them.
-constexpr int MAX_DEVS = 16;
 std::mutex g_dev_mu[MAX_DEVS];
 std::shared_ptr<Context> g_ctx;
 int g_algo = PQH_ALGO_AUTO;
@@ -209,8 +229,32 @@ int parse_env_devices(std::vector<int> &out) {
     return PQH_OK;
 }
 
+void release_merge(Context *c) {
+    MergeState &ms = c->merge;
+    if (c->devs.empty() || cudaSetDevice(c->devs[0].dev) != cudaSuccess) return;
+    if (ms.stream) cudaStreamSynchronize(ms.stream);
+    ms.heaps.release();
+    ms.work.release();
+    ms.out_ids.release();
+    ms.out_dists.release();
+    ms.peer_ids.release();
+    ms.peer_assign.release();
+    ms.peer_dis.release();
+    for (int g = 0; g < MAX_DEVS; ++g) {
+        if (ms.searched[g]) cudaEventDestroy(ms.searched[g]);
+        if (ms.consumed[g]) cudaEventDestroy(ms.consumed[g]);
+        ms.searched[g] = ms.consumed[g] = nullptr;
+    }
+    if (ms.stream) cudaStreamDestroy(ms.stream);
+    ms.stream = nullptr;
+    ms.n = 0;
+    ms.k = 0;
+    ms.next_ticket = 0;
+}
+
 void destroy_ctx(Context *c) {
     if (!c) return;
+    release_merge(c);
     for (size_t g = 0; g < c->devs.size(); ++g) {
         DeviceCtx &d = c->devs[g];
         std::lock_guard<std::mutex> dev_lock(g_dev_mu[g]);
@@ -321,9 +365,30 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+// the exact kernel runs over at most this many rows per launch, so its per-row lists stay
+// bounded whatever n is (10M rows x k = 33 would otherwise ask for 10 GB)
+constexpr int EXACT_CHUNK_ROWS = 1 << 18;
+
 size_t exact_ws(int n_rows, int nb, int k, int num_sms) {
     (void)nb;
-    return pqh::exact_workspace_bound(n_rows, k > 1 ? k : 1, num_sms);
+    return pqh::exact_workspace_bound(n_rows < EXACT_CHUNK_ROWS ? n_rows : EXACT_CHUNK_ROWS,
+                                      k > 1 ? k : 1, num_sms);
+}
+
+// exact kernel over rows [q_begin, q_begin + n_rows) or over the listed absolute ids, in chunks
+cudaError_t exact_chunked(const float *d_b, const float *d_v, const int *d_row_ids, int q_begin,
+                          int q_row0, int out_q_begin, int n_rows, int nb, int d, int k,
+                          int self_join, int *d_assign, float *d_dis, void *d_work,
+                          size_t work_bytes, int num_sms, cudaStream_t stream, int *launches) {
+    for (int done = 0; done < n_rows; done += EXACT_CHUNK_ROWS) {
+        const int n = n_rows - done < EXACT_CHUNK_ROWS ? n_rows - done : EXACT_CHUNK_ROWS;
+        cudaError_t e = pqh::launch_knn_exact(d_b, d_v, d_row_ids ? d_row_ids + done : nullptr,
+                                              d_row_ids ? 0 : q_begin + done, q_row0, out_q_begin,
+                                              n, nb, d, k, self_join, d_assign, d_dis, d_work,
+                                              work_bytes, num_sms, stream, launches);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 size_t align1k(size_t x) { return (x + 1023) & ~(size_t)1023; }
@@ -493,19 +558,19 @@ int search_on_device(DeviceCtx &dc, int algo, int nb, int d, int k, const float 
         if (n_fb > 0) {
             rows_ex = n_fb;
             CU_TRY(cudaEventRecord(dc.xev[0], stream));
-            CU_TRY(pqh::launch_knn_exact(d_b, d_v, d_fb_rows, 0, q_row0, q_begin, (int)n_fb, nb, d,
-                                         k, self_join, d_assign, d_dis,
-                                         static_cast<unsigned char *>(d_work) + tcb,
-                                         work_bytes - tcb, dc.num_sms, stream, &launches));
+            CU_TRY(exact_chunked(d_b, d_v, d_fb_rows, 0, q_row0, q_begin, (int)n_fb, nb, d, k,
+                                 self_join, d_assign, d_dis,
+                                 static_cast<unsigned char *>(d_work) + tcb, work_bytes - tcb,
+                                 dc.num_sms, stream, &launches));
             CU_TRY(cudaEventRecord(dc.xev[1], stream));
             exact_timed = true;
         }
     } else {
         rows_ex = n_rows;
         CU_TRY(cudaEventRecord(dc.xev[0], stream));
-        CU_TRY(pqh::launch_knn_exact(d_b, d_v, nullptr, q_begin, q_row0, q_begin, n_rows, nb, d, k,
-                                     self_join, d_assign, d_dis, d_work, work_bytes, dc.num_sms,
-                                     stream, &launches));
+        CU_TRY(exact_chunked(d_b, d_v, nullptr, q_begin, q_row0, q_begin, n_rows, nb, d, k,
+                             self_join, d_assign, d_dis, d_work, work_bytes, dc.num_sms, stream,
+                             &launches));
         CU_TRY(cudaEventRecord(dc.xev[1], stream));
         exact_timed = true;
     }
@@ -621,6 +686,84 @@ __global__ void gather_block_rows_kernel(const float *__restrict__ data, const i
     }
 }
 
+// ---- device-side merge: the reference's k-slot max-heap, one thread per row ---------------------
+// (fast_nn_temp_file.c:11-63; restated for the host in host/pqh_compute_nn_fast.c, which is the
+// checker for these kernels: tests compare the heap image and both result files byte by byte)
+struct HeapItem {
+    unsigned id;
+    float dist;
+};
+
+// Put x into the hole at the root of heap[0..n) and let it sink: at each level the larger child
+// moves up when it is farther than x; the right child is only preferred when strictly farther
+// than the left one (fast_nn_heap_push_impl, fast_nn_temp_file.c:23-46).
+__device__ __forceinline__ void heap_sink_from_root(HeapItem *heap, int n, HeapItem x) {
+    int hole = 0;
+    for (;;) {
+        const int left = 2 * hole + 1, right = left + 1;
+        int pick = -1;
+        if (right < n && heap[right].dist > heap[left].dist && heap[right].dist > x.dist)
+            pick = right;
+        else if (left < n && heap[left].dist > x.dist)
+            pick = left;
+        if (pick < 0) break;
+        heap[hole] = heap[pick];
+        hole = pick;
+    }
+    heap[hole] = x;
+}
+
+// run_merge_block (compute_nn_fast.c:485-508) for one searched block: row r of the block is
+// vector row_ids[r]; its neighbours in columns 1 .. k1-1 (column 0 is the row itself) are
+// offered, in column order, to that vector's heap: dropped when not strictly nearer than the
+// current worst or already present (fast_nn_heap_push, fast_nn_temp_file.c:48-54).
+__global__ void merge_block_kernel(HeapItem *__restrict__ heaps, int k,
+                                   const int *__restrict__ row_ids, int m,
+                                   const int *__restrict__ assign, const float *__restrict__ dis,
+                                   int k1) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    HeapItem *heap = heaps + (size_t)row_ids[r] * k;
+    const int *ai = assign + (size_t)r * k1;
+    const float *di = dis + (size_t)r * k1;
+    for (int c = 1; c < k1; ++c) {
+        if (ai[c] < 0) continue;  // unfilled tail of a row
+        HeapItem x;
+        x.id = (unsigned)row_ids[ai[c]];
+        x.dist = di[c];
+        if (x.dist >= heap[0].dist) continue;  // ties lose
+        bool present = false;
+        for (int i = 0; i < k; ++i) present |= heap[i].id == x.id;
+        if (present) continue;
+        heap_sink_from_root(heap, k, x);
+    }
+}
+
+__global__ void heaps_clear_kernel(HeapItem *heaps, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        heaps[i].id = 0xFFFFFFFFu;                 // init_temp_file, fast_nn_temp_file.c:97-100
+        heaps[i].dist = __int_as_float(0x7f800000);
+    }
+}
+
+// temp_file_to_result / fast_nn_heap_sort (fast_nn_temp_file.c:56-63): extract-max k times on
+// a COPY of each heap (the image itself is what --no-delete-temp-file keeps)
+__global__ void heaps_drain_kernel(const HeapItem *__restrict__ heaps, HeapItem *__restrict__ work,
+                                   long long n, int k, unsigned *__restrict__ ids,
+                                   float *__restrict__ dists) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const HeapItem *src = heaps + (size_t)r * k;
+    HeapItem *h = work + (size_t)r * k;
+    for (int i = 0; i < k; ++i) h[i] = src[i];
+    for (int len = k - 1; len >= 0; --len) {
+        ids[(size_t)r * k + len] = h[0].id;
+        dists[(size_t)r * k + len] = h[0].dist;
+        heap_sink_from_root(h, len, h[len]);
+    }
+}
+
 // Self-join among rows `row_ids` of the data set resident on device slot `slot` (host pointers
 // in and out).
 int dataset_search_block(Context *c, int slot, int algo, int m, const int *row_ids, int k,
@@ -655,10 +798,12 @@ int dataset_search_block(Context *c, int slot, int algo, int m, const int *row_i
     if (rc) return rc;
     if (st) ++st->launches;
     CU_TRY(cudaEventRecord(dc.ev[2], dc.stream));
-    CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int), cudaMemcpyDeviceToHost,
-                           dc.stream));
-    CU_TRY(cudaMemcpyAsync(dis, dc.dis.p, out_elems * sizeof(float), cudaMemcpyDeviceToHost,
-                           dc.stream));
+    if (assign) {  // null: the results stay on the device for the device-side merge
+        CU_TRY(cudaMemcpyAsync(assign, dc.assign.p, out_elems * sizeof(int),
+                               cudaMemcpyDeviceToHost, dc.stream));
+        CU_TRY(cudaMemcpyAsync(dis, dc.dis.p, out_elems * sizeof(float), cudaMemcpyDeviceToHost,
+                               dc.stream));
+    }
     CU_TRY(cudaEventRecord(dc.ev[3], dc.stream));
     CU_TRY(cudaStreamSynchronize(dc.stream));
     if (st) {
@@ -667,6 +812,45 @@ int dataset_search_block(Context *c, int slot, int algo, int m, const int *row_i
         st->ms_d2h += ev_ms(dc.ev[2], dc.ev[3]);
         if (st->rows_exact > 0) st->ms_exact += ev_ms(dc.xev[0], dc.xev[1]);
     }
+    return PQH_OK;
+}
+
+void add_block_stats(Context *c, const pqh_knn_stats_t &st, double ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    pqh_knn_stats_t &a = c->stats;
+    a.rows += st.rows;
+    a.rows_tensor += st.rows_tensor;
+    a.rows_exact += st.rows_exact;
+    a.rows_second_pass += st.rows_second_pass;
+    a.launches += st.launches;
+    a.ms_total += ms;
+    a.ms_h2d += st.ms_h2d;
+    a.ms_kernels += st.ms_kernels;
+    a.ms_d2h += st.ms_d2h;
+    a.ms_prep += st.ms_prep;
+    a.ms_gemm += st.ms_gemm;
+    a.ms_rerank += st.ms_rerank;
+    a.ms_exact += st.ms_exact;
+    a.candidates += st.candidates;
+    if (st.eps_ratio_max > a.eps_ratio_max) a.eps_ratio_max = st.eps_ratio_max;
+    a.inexact_operands |= st.inexact_operands;
+}
+
+int check_block_args(Context *c, int slot, int m, const int *row_ids, int k) {
+    if (!c) return fail(PQH_EINVAL, "no data set loaded");
+    if (slot < 0 || slot >= (int)c->devs.size())
+        return fail(PQH_EINVAL, "device slot %d out of range (context has %zu)", slot,
+                    c->devs.size());
+    if (m < 0 || k < 0 || (m > 0 && !row_ids)) return fail(PQH_EINVAL, "bad block m=%d k=%d", m, k);
+    return PQH_OK;
+}
+
+int check_block_rows(const DeviceCtx &dc, int m, const int *row_ids) {
+    if (dc.ds_d <= 0) return fail(PQH_EINVAL, "no data set loaded");
+    for (int i = 0; i < m; ++i)
+        if (row_ids[i] < 0 || row_ids[i] >= dc.ds_n)
+            return fail(PQH_EINVAL, "row id %d at position %d outside the data set (%d rows)",
+                        row_ids[i], i, dc.ds_n);
     return PQH_OK;
 }
 
@@ -904,47 +1088,183 @@ int pqh_knn_dataset_search_block(int slot, int m, const int *row_ids, int k, int
         algo = g_algo;
     }
     Context *c = ctx.get();
-    if (!c) return fail(PQH_EINVAL, "no data set loaded");
-    if (slot < 0 || slot >= (int)c->devs.size())
-        return fail(PQH_EINVAL, "device slot %d out of range (context has %zu)", slot,
-                    c->devs.size());
-    DeviceCtx &dc = c->devs[slot];
-    if (m < 0 || k < 0 || (m > 0 && (!row_ids || (k > 0 && (!assign || !dis)))))
-        return fail(PQH_EINVAL, "bad block m=%d k=%d", m, k);
+    int rc = check_block_args(c, slot, m, row_ids, k);
+    if (rc) return rc;
+    if (m > 0 && k > 0 && (!assign || !dis)) return fail(PQH_EINVAL, "null output pointer");
     pqh_knn_stats_t st;
     memset(&st, 0, sizeof(st));
     auto t0 = std::chrono::steady_clock::now();
-    int rc;
     {
         std::lock_guard<std::mutex> dev_lock(g_dev_mu[slot]);
-        if (dc.ds_d <= 0) return fail(PQH_EINVAL, "no data set loaded");
-        for (int i = 0; i < m; ++i)
-            if (row_ids[i] < 0 || row_ids[i] >= dc.ds_n)
-                return fail(PQH_EINVAL, "row id %d at position %d outside the data set (%d rows)",
-                            row_ids[i], i, dc.ds_n);
+        if ((rc = check_block_rows(c->devs[slot], m, row_ids))) return rc;
         rc = dataset_search_block(c, slot, algo, m, row_ids, k, assign, dis, &st);
     }
-    const double ms =
-        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::lock_guard<std::mutex> lock(g_mu);
-    pqh_knn_stats_t &a = c->stats;
-    a.rows += st.rows;
-    a.rows_tensor += st.rows_tensor;
-    a.rows_exact += st.rows_exact;
-    a.rows_second_pass += st.rows_second_pass;
-    a.launches += st.launches;
-    a.ms_total += ms;
-    a.ms_h2d += st.ms_h2d;
-    a.ms_kernels += st.ms_kernels;
-    a.ms_d2h += st.ms_d2h;
-    a.ms_prep += st.ms_prep;
-    a.ms_gemm += st.ms_gemm;
-    a.ms_rerank += st.ms_rerank;
-    a.ms_exact += st.ms_exact;
-    a.candidates += st.candidates;
-    if (st.eps_ratio_max > a.eps_ratio_max) a.eps_ratio_max = st.eps_ratio_max;
-    a.inexact_operands |= st.inexact_operands;
+    add_block_stats(c, st, std::chrono::duration<double, std::milli>(
+                               std::chrono::steady_clock::now() - t0).count());
     return rc;
+}
+
+int pqh_knn_heaps_create(long long n, int k, const void *image) {
+    if (n < 0 || k <= 0) return fail(PQH_EINVAL, "bad heap shape n=%lld k=%d", n, k);
+    std::shared_ptr<Context> ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    Context *c = ctx.get();
+    MergeState &ms = c->merge;
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[0]);
+    release_merge(c);
+    DeviceCtx &d0 = c->devs[0];
+    CU_TRY(cudaSetDevice(d0.dev));
+    const size_t total = (size_t)n * k;
+    if ((rc = ms.heaps.ensure(total * sizeof(HeapItem) + 8))) return rc;
+    CU_TRY(cudaStreamCreateWithFlags(&ms.stream, cudaStreamNonBlocking));
+    if (image) {
+        if ((rc = h2d_rows(d0, static_cast<float *>(ms.heaps.p), static_cast<const float *>(image),
+                           2, 2, total)))  // an item is two 4-byte words
+            return rc;
+        CU_TRY(cudaStreamSynchronize(d0.stream));
+    } else if (total) {
+        heaps_clear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ms.stream>>>(
+            static_cast<HeapItem *>(ms.heaps.p), total);
+        CU_TRY(cudaGetLastError());
+    }
+    for (size_t g = 0; g < c->devs.size(); ++g) {
+        CU_TRY(cudaSetDevice(c->devs[g].dev));
+        CU_TRY(cudaEventCreateWithFlags(&ms.searched[g], cudaEventDisableTiming));
+        CU_TRY(cudaSetDevice(d0.dev));
+        CU_TRY(cudaEventCreateWithFlags(&ms.consumed[g], cudaEventDisableTiming));
+    }
+    ms.n = n;
+    ms.k = k;
+    ms.next_ticket = 0;
+    return PQH_OK;
+}
+
+int pqh_knn_dataset_search_block_merge(int slot, int m, const int *row_ids, int k1,
+                                       long long ticket) {
+    std::shared_ptr<Context> ctx;
+    int algo;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        ctx = g_ctx;
+        algo = g_algo;
+    }
+    Context *c = ctx.get();
+    int rc = check_block_args(c, slot, m, row_ids, k1);
+    if (rc) return rc;
+    MergeState &ms = c->merge;
+    if (ms.k <= 0) return fail(PQH_EINVAL, "no heaps: call pqh_knn_heaps_create first");
+    if (ticket < 0) return fail(PQH_EINVAL, "bad ticket %lld", ticket);
+    DeviceCtx &dc = c->devs[slot];
+    pqh_knn_stats_t st;
+    memset(&st, 0, sizeof(st));
+    auto t0 = std::chrono::steady_clock::now();
+    const bool work = m > 1 && k1 > 1;  // a block of one row has no neighbours to offer
+    if (work) {
+        std::lock_guard<std::mutex> dev_lock(g_dev_mu[slot]);
+        if ((rc = check_block_rows(dc, m, row_ids)) == PQH_OK) {
+            for (int i = 0; i < m && rc == PQH_OK; ++i)
+                if (row_ids[i] >= ms.n)
+                    rc = fail(PQH_EINVAL, "row id %d beyond the %lld heaps", row_ids[i], ms.n);
+        }
+        if (rc == PQH_OK) {
+            auto run = [&]() -> int {
+                CU_TRY(cudaSetDevice(dc.dev));
+                // the merge of this device's previous block must have read its result buffers
+                CU_TRY(cudaStreamWaitEvent(dc.stream, ms.consumed[slot], 0));
+                int r = dataset_search_block(c, slot, algo, m, row_ids, k1, nullptr, nullptr, &st);
+                if (r) return r;
+                CU_TRY(cudaEventRecord(ms.searched[slot], dc.stream));
+                return PQH_OK;
+            };
+            rc = run();
+        }
+    }
+    // merges happen in ticket order, whatever device searched the block and however long it took
+    {
+        std::unique_lock<std::mutex> lk(ms.mu);
+        ms.cv.wait(lk, [&] { return ms.next_ticket == ticket; });
+        if (work && rc == PQH_OK) {
+            auto run = [&]() -> int {
+                DeviceCtx &d0 = c->devs[0];
+                CU_TRY(cudaSetDevice(d0.dev));
+                CU_TRY(cudaStreamWaitEvent(ms.stream, ms.searched[slot], 0));
+                const int *d_ids = static_cast<const int *>(dc.block_ids.p);
+                const int *d_assign = static_cast<const int *>(dc.assign.p);
+                const float *d_dis = static_cast<const float *>(dc.dis.p);
+                if (slot != 0) {
+                    const size_t nb_ids = (size_t)m * sizeof(int), nb_out = (size_t)m * k1 * 4;
+                    int r;
+                    if ((r = ms.peer_ids.ensure(nb_ids))) return r;
+                    if ((r = ms.peer_assign.ensure(nb_out))) return r;
+                    if ((r = ms.peer_dis.ensure(nb_out))) return r;
+                    CU_TRY(cudaMemcpyPeerAsync(ms.peer_ids.p, d0.dev, d_ids, dc.dev, nb_ids, ms.stream));
+                    CU_TRY(cudaMemcpyPeerAsync(ms.peer_assign.p, d0.dev, d_assign, dc.dev, nb_out,
+                                               ms.stream));
+                    CU_TRY(cudaMemcpyPeerAsync(ms.peer_dis.p, d0.dev, d_dis, dc.dev, nb_out,
+                                               ms.stream));
+                    d_ids = static_cast<const int *>(ms.peer_ids.p);
+                    d_assign = static_cast<const int *>(ms.peer_assign.p);
+                    d_dis = static_cast<const float *>(ms.peer_dis.p);
+                }
+                merge_block_kernel<<<(m + 127) / 128, 128, 0, ms.stream>>>(
+                    static_cast<HeapItem *>(ms.heaps.p), ms.k, d_ids, m, d_assign, d_dis, k1);
+                CU_TRY(cudaGetLastError());
+                CU_TRY(cudaEventRecord(ms.consumed[slot], ms.stream));
+                return PQH_OK;
+            };
+            rc = run();
+        }
+        ++ms.next_ticket;
+        ms.cv.notify_all();
+    }
+    add_block_stats(c, st, std::chrono::duration<double, std::milli>(
+                               std::chrono::steady_clock::now() - t0).count());
+    return rc;
+}
+
+int pqh_knn_heaps_export(void *image, unsigned *ids, float *dists) {
+    std::shared_ptr<Context> ctx;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        ctx = g_ctx;
+    }
+    Context *c = ctx.get();
+    if (!c || c->merge.k <= 0) return fail(PQH_EINVAL, "no heaps");
+    MergeState &ms = c->merge;
+    DeviceCtx &d0 = c->devs[0];
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[0]);
+    CU_TRY(cudaSetDevice(d0.dev));
+    CU_TRY(cudaStreamSynchronize(ms.stream));
+    const size_t total = (size_t)ms.n * ms.k;
+    int rc;
+    if (image && (rc = d2h_bytes(d0, image, ms.heaps.p, total * sizeof(HeapItem)))) return rc;
+    if (ids || dists) {
+        if (!ids || !dists) return fail(PQH_EINVAL, "ids and dists go together");
+        if ((rc = ms.work.ensure(total * sizeof(HeapItem) + 8))) return rc;
+        if ((rc = ms.out_ids.ensure(total * sizeof(unsigned) + 8))) return rc;
+        if ((rc = ms.out_dists.ensure(total * sizeof(float) + 8))) return rc;
+        if (ms.n > 0) {
+            heaps_drain_kernel<<<(unsigned)((ms.n + 127) / 128), 128, 0, d0.stream>>>(
+                static_cast<const HeapItem *>(ms.heaps.p), static_cast<HeapItem *>(ms.work.p), ms.n,
+                ms.k, static_cast<unsigned *>(ms.out_ids.p), static_cast<float *>(ms.out_dists.p));
+            CU_TRY(cudaGetLastError());
+        }
+        if ((rc = d2h_bytes(d0, ids, ms.out_ids.p, total * sizeof(unsigned)))) return rc;
+        if ((rc = d2h_bytes(d0, dists, ms.out_dists.p, total * sizeof(float)))) return rc;
+    }
+    return PQH_OK;
+}
+
+void pqh_knn_heaps_release(void) {
+    std::shared_ptr<Context> ctx;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        ctx = g_ctx;
+    }
+    if (!ctx) return;
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[0]);
+    release_merge(ctx.get());
 }
 
 void pqh_knn_dataset_release(void) {

@@ -222,15 +222,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[
 __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// the same wait, naming the registers of a pending 16-column load as in/out operands so that
-// the compiler cannot schedule their first use above the wait
-__device__ __forceinline__ void tmem_wait_ld_16(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
-
 // ---- thread-block cluster / CTA-pair (cta_group::2) variants ----------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

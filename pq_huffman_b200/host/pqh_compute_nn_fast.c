@@ -24,8 +24,11 @@
  * Modes: --num-dims 0 is the exact search (one block = the whole data set, handed to
  * pqh_knn_search_rows_ld as the .fvecs image itself, leading dimension d+1); --num-dims S > 0
  * (the reference's default is 5) is its approximate mode over blocks_per_dim^S overlapping boxes
- * (pqh_partition.h).  There the GPU searches block b+1 (one host thread per device of
- * $PQH_DEVICES) while the host cores merge block b.  --blocks-from / --blocks-to select a range
+ * (pqh_partition.h).  There the blocks are searched by one host thread per device of
+ * $PQH_DEVICES and merged ON THE DEVICE, in block order, into heaps resident in HBM
+ * (pqh_knn_heaps_*: a block's result never travels to the host; --host-merge keeps the heaps
+ * here and merges block b on the host cores while the GPU searches block b+1 -- the checker
+ * for the device kernels).  --blocks-from / --blocks-to select a range
  * with the reference's arithmetic (compute_nn_fast.c:545-555, which leaves an EMPTY range for any
  * --blocks-to inside the range); --num-dimensions-at-pass only groups blocks and cannot change
  * the result.  The search itself is libpqh_knn.so -- no CPU fallback.
@@ -54,7 +57,7 @@ typedef struct {
 typedef struct {
     const char *input, *tpl, *temp_file;
     const char *blocks_info_cache;
-    int num_nn, num_dims, delete_temp, init_temp, with_blocks_stat, num_threads;
+    int num_nn, num_dims, delete_temp, init_temp, with_blocks_stat, num_threads, host_merge;
     int blocks_per_dim, dims_on_pass;
     double overlap;
     long long blocks_from, blocks_to;
@@ -72,7 +75,8 @@ static void usage(const char *argv0) {
             "  [--num-dims S] [--num-blocks-per-dim B] [--block-overlap-fraction F]\n"
             "  [--blocks-info-cache FILE] [--temp-file FILE] [--no-init-temp-file]\n"
             "  [--no-delete-temp-file] [--blocks-from I] [--blocks-to J] [--with-blocks-stat]\n"
-            "  [--num-threads T] [--num-dimensions-at-pass P]   (the reference's flags)\n",
+            "  [--num-threads T] [--num-dimensions-at-pass P]   (the reference's flags)\n"
+            "  [--host-merge]   merge the blocks on the host cores instead of on the device\n",
             argv0);
 }
 
@@ -98,6 +102,7 @@ static options_t parse(int argc, char **argv) {
     o.num_dims = 5; /* the reference's default is the partitioned mode */
     o.delete_temp = 1;
     o.init_temp = 1;
+    o.host_merge = 0;
     o.with_blocks_stat = 0;
     o.num_threads = 0; /* 0: flag absent -> every core this process may run on */
     o.blocks_info_cache = NULL;
@@ -117,6 +122,7 @@ static options_t parse(int argc, char **argv) {
         else if (!strcmp(a, "--temp-file") && i + 1 < argc) o.temp_file = argv[++i];
         else if (!strcmp(a, "--num-dims") && i + 1 < argc) o.num_dims = atoi(argv[++i]);
         else if (!strcmp(a, "--num-threads") && i + 1 < argc) o.num_threads = atoi(argv[++i]);
+        else if (!strcmp(a, "--host-merge")) o.host_merge = 1;
         else if (!strcmp(a, "--blocks-info-cache") && i + 1 < argc) o.blocks_info_cache = argv[++i];
         else if (!strcmp(a, "--block-overlap-fraction") && i + 1 < argc) o.overlap = atof(argv[++i]);
         else if (!strcmp(a, "--num-blocks-per-dim") && i + 1 < argc) o.blocks_per_dim = atoi(argv[++i]);
@@ -331,6 +337,7 @@ typedef struct {
     int prefix_len, k, threads;
     FILE *blocks_stat;
     double t_rows;
+    int device_merge; /* blocks are merged into heaps resident on the device, in block order */
 } pipeline_t;
 
 typedef struct {
@@ -346,25 +353,38 @@ static void *device_thread(void *arg) {
         pthread_mutex_lock(&pl->mu);
         while (s->state != SLOT_READY) pthread_cond_wait(&pl->cv, &pl->mu);
         pthread_mutex_unlock(&pl->mu);
-        const long long need = s->m * s->k1;
-        if (need > s->cap) {
-            pqh_knn_host_free(s->assign);
-            pqh_knn_host_free(s->dis);
-            s->cap = need + need / 4 + 1024;
-            s->assign = (int *)pqh_knn_host_alloc(s->cap * (long long)sizeof(int));
-            s->dis = (float *)pqh_knn_host_alloc(s->cap * (long long)sizeof(float));
-            if (!s->assign || !s->dis) {
-                fprintf(stderr, "cannot allocate %lld result slots: %s\n", s->cap, pqh_last_error());
-                exit(1);
-            }
-        }
-        if (s->m > 1) { /* a block of one row has no neighbours to offer */
-            int rc = pqh_knn_dataset_search_block(dt->device_slot, (int)s->m, s->ids, s->k1,
-                                                  s->assign, s->dis);
+        if (pl->device_merge) {
+            /* search + run_merge_block on the device; the ticket keeps the merges in block order
+             * across devices (blocks of one row only take their turn) */
+            int rc = pqh_knn_dataset_search_block_merge(dt->device_slot, (int)s->m, s->ids, s->k1,
+                                                        b - pl->begin);
             if (rc != PQH_OK) {
-                fprintf(stderr, "block %lld: pqh_knn_dataset_search_block failed: %s\n", b,
+                fprintf(stderr, "block %lld: pqh_knn_dataset_search_block_merge failed: %s\n", b,
                         pqh_last_error());
                 exit(1);
+            }
+        } else {
+            const long long need = s->m * s->k1;
+            if (need > s->cap) {
+                pqh_knn_host_free(s->assign);
+                pqh_knn_host_free(s->dis);
+                s->cap = need + need / 4 + 1024;
+                s->assign = (int *)pqh_knn_host_alloc(s->cap * (long long)sizeof(int));
+                s->dis = (float *)pqh_knn_host_alloc(s->cap * (long long)sizeof(float));
+                if (!s->assign || !s->dis) {
+                    fprintf(stderr, "cannot allocate %lld result slots: %s\n", s->cap,
+                            pqh_last_error());
+                    exit(1);
+                }
+            }
+            if (s->m > 1) { /* a block of one row has no neighbours to offer */
+                int rc = pqh_knn_dataset_search_block(dt->device_slot, (int)s->m, s->ids, s->k1,
+                                                      s->assign, s->dis);
+                if (rc != PQH_OK) {
+                    fprintf(stderr, "block %lld: pqh_knn_dataset_search_block failed: %s\n", b,
+                            pqh_last_error());
+                    exit(1);
+                }
             }
         }
         pthread_mutex_lock(&pl->mu);
@@ -507,8 +527,11 @@ int main(int argc, char **argv) {
         return 1;
     }
     heaps_arg_t ha = {heaps, n, k, out_ids, out_dists};
+    /* partitioned mode: the heaps live on the device and the blocks are merged there
+     * (pqh_knn_heaps_*); --host-merge keeps them here, merged by the host cores */
+    const int device_merge = !(n == 0 || o.num_dims == 0) && !o.host_merge;
     if (o.init_temp) {
-        parallel(nt, clear_heaps_part, &ha);
+        if (!device_merge) parallel(nt, clear_heaps_part, &ha);
     } else {
         FILE *tf = fopen(o.temp_file, "rb");
         if (!tf || fread(heaps, sizeof(slot_t), (size_t)n * k, tf) != (size_t)n * k) {
@@ -597,7 +620,12 @@ int main(int argc, char **argv) {
             fprintf(stderr, "pqh_knn_dataset_load failed: %s\n", pqh_last_error());
             return 1;
         }
+        if (device_merge && pqh_knn_heaps_create(n, k, o.init_temp ? NULL : heaps) != PQH_OK) {
+            fprintf(stderr, "pqh_knn_heaps_create failed: %s\n", pqh_last_error());
+            return 1;
+        }
         pipeline_t pl;
+        pl.device_merge = device_merge;
         pthread_mutex_init(&pl.mu, NULL);
         pthread_cond_init(&pl.cv, NULL);
         pl.num_devices = pqh_knn_device_count();
@@ -639,7 +667,7 @@ int main(int argc, char **argv) {
             pthread_mutex_unlock(&pl.mu);
             const double tm = now_s();
             t_wait_gpu += tm - tw;
-            if (s->m > 1)
+            if (s->m > 1 && !device_merge)
                 merge_block(merge_threads, heaps, k, s->k1, s->m, s->ids, s->assign, s->dis);
             t_merge_only += now_s() - tm;
             rows_in_blocks += s->m;
@@ -666,7 +694,17 @@ int main(int argc, char **argv) {
     free(cols);
 
     /* ---- export, as the reference does from its temp file (temp_file_to_result) ---- */
-    parallel(nt, export_heaps_part, &ha);
+    if (device_merge && n > 0 && begin < end) {
+        /* heap-sorted rows (and the heap image, if the temp file is kept) from the device */
+        if (pqh_knn_heaps_export(o.delete_temp ? NULL : heaps, out_ids, out_dists) != PQH_OK) {
+            fprintf(stderr, "pqh_knn_heaps_export failed: %s\n", pqh_last_error());
+            return 1;
+        }
+        pqh_knn_heaps_release();
+    } else {
+        if (device_merge && o.init_temp) parallel(nt, clear_heaps_part, &ha); /* no block ran */
+        parallel(nt, export_heaps_part, &ha);
+    }
     char *pi = join(o.tpl, "nn_indices.ivecsl"), *pd = join(o.tpl, "nn_dist.fvecsl");
     write_light(pi, out_ids, sizeof(uint32_t), n, k);
     write_light(pd, out_dists, sizeof(float), n, k);

@@ -150,3 +150,42 @@ def dataset_search_block(row_ids, k, slot=0):
 
 def dataset_release():
     _lib.load().pqh_knn_dataset_release()
+
+
+# ---- device-side merge of the partitioned mode (pqh_knn_heaps_*) ----
+ITEM = np.dtype([("id", "<u4"), ("dist", "<f4")])   # nn_item_t, fast_nn_temp_file.h:11-14
+
+
+def heaps_create(n, k, image=None):
+    """n heaps of k items on the device; ``image`` = an existing temp-file image (ITEM[n*k])."""
+    lib = _lib.load()
+    if image is not None:
+        image = np.ascontiguousarray(image, dtype=ITEM)
+        assert image.size == n * k
+        _check(lib.pqh_knn_heaps_create(n, k, image.ctypes.data))
+    else:
+        _check(lib.pqh_knn_heaps_create(n, k, None))
+
+
+def dataset_search_block_merge(row_ids, k1, ticket, slot=0):
+    """Search the block ``row_ids`` of the resident data set and merge it into the heaps on the
+    device (run_block + run_merge_block, compute_nn_fast.c:469-508); merges happen in ticket order."""
+    lib = _lib.load()
+    ids = np.ascontiguousarray(row_ids, dtype=np.int32)
+    _check(lib.pqh_knn_dataset_search_block_merge(slot, ids.shape[0], ids.ctypes.data, k1, ticket))
+
+
+def heaps_export(n, k, want_image=True):
+    """(image ITEM[n,k] or None, ids uint32[n,k], dists float32[n,k]) as the reference's temp file
+    and result files hold them."""
+    lib = _lib.load()
+    image = np.empty((n, k), dtype=ITEM) if want_image else None
+    ids = np.empty((n, k), dtype=np.uint32)
+    dists = np.empty((n, k), dtype=np.float32)
+    _check(lib.pqh_knn_heaps_export(image.ctypes.data if want_image else None, ids.ctypes.data,
+                                    dists.ctypes.data))
+    return image, ids, dists
+
+
+def heaps_release():
+    _lib.load().pqh_knn_heaps_release()

@@ -47,14 +47,16 @@ def _check_rows_against_oracle(x, a, dist, k, rows):
         assert np.array_equal(dist[r].view(np.uint32), ed[0].view(np.uint32)), f"row {r}: distances"
 
 
-def _sampled_and_uncertified(n, n_sample, seed, cap=400):
+def _sampled_and_uncertified(n, n_sample, seed, cap=1500):
+    """n_sample random rows plus the rows the first pass left open (all of them up to `cap`)."""
     rng = np.random.default_rng(seed)
     rows = set(int(r) for r in rng.choice(n, n_sample, replace=False))
     fb = knn.last_fallback_rows()
-    if len(fb) > cap:   # never the case on these data sets; keep the test bounded anyway
+    n_fb = len(fb)
+    if n_fb > cap:
         fb = rng.choice(fb, cap, replace=False)
     rows.update(int(r) for r in fb)
-    return sorted(rows), len(fb)
+    return sorted(rows), n_fb
 
 
 def test_full_size_gist1m():
@@ -68,7 +70,7 @@ def test_full_size_gist1m():
     assert st["inexact_operands"] == 1
     _check_properties(a, dist, n)
     rows, n_fb = _sampled_and_uncertified(n, 32, seed=3)
-    assert n_fb == st["rows_second_pass"] or st["rows_second_pass"] == 0
+    assert n_fb >= st["rows_second_pass"]      # second-pass rows are first-pass failures
     _check_rows_against_oracle(x, a, dist, k, rows)
 
 

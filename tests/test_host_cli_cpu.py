@@ -29,21 +29,24 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("merge", [[], ["--host-merge"]], ids=["device-merge-api", "host-merge"])
 @pytest.mark.parametrize("gen,n,d,k,flags", CASES)
-def test_partitioned_mode_bytes(tmp_path, gen, n, d, k, flags):
+def test_partitioned_mode_bytes(tmp_path, gen, n, d, k, flags, merge):
+    """Default: the blocks go through pqh_knn_heaps_* / ..._search_block_merge (the stand-in
+    implements them on the CPU); --host-merge: the driver's own heap code merges them."""
     x = make_golden.make_input(gen, n, d, 70 + n)
     inp = str(tmp_path / "in.fvecs")
     vecs_io.write_xvecs(inp, x, "f")
     extra = [*flags, "--no-delete-temp-file", "--with-blocks-stat"]
     ours, out = _run_partitioned(SHIM, inp, tmp_path / "ours", k,
-                                 [*extra, "--blocks-info-cache", str(tmp_path / "ours.cache")])
+                                 [*extra, *merge, "--blocks-info-cache", str(tmp_path / "ours.cache")])
     ref, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref", k,
                               [*extra, "--blocks-info-cache", str(tmp_path / "ref.cache")])
     for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs", "blocks_stat.txt"):
         assert _sha(ours + name) == _sha(ref + name), f"{name} differs"
     assert _sha(str(tmp_path / "ours.cache")) == _sha(str(tmp_path / "ref.cache"))
     again, out2 = _run_partitioned(SHIM, inp, tmp_path / "again", k,
-                                   [*flags, "--blocks-info-cache", str(tmp_path / "ref.cache")])
+                                   [*flags, *merge, "--blocks-info-cache", str(tmp_path / "ref.cache")])
     assert "Blocks info: Loaded" in out2
     assert _sha(again + "nn_indices.ivecsl") == _sha(ref + "nn_indices.ivecsl")
     assert not os.path.exists(again + "tmp.vecs")
@@ -59,13 +62,15 @@ def test_single_block_mode_bytes(tmp_path):
         assert _sha(ours + name) == _sha(ref + name), f"{name} differs"
 
 
-def test_resume_from_temp_file_bytes(tmp_path):
+@pytest.mark.parametrize("merge", [[], ["--host-merge"]], ids=["device-merge-api", "host-merge"])
+def test_resume_from_temp_file_bytes(tmp_path, merge):
     n, d, k = 4000, 12, 10
     x = make_golden.make_input("sift_like", n, d, 5)
     inp = str(tmp_path / "in.fvecs")
     vecs_io.write_xvecs(inp, x, "f")
     flags = ["--num-dims", "2", "--no-delete-temp-file"]
-    ours, _ = _run_partitioned(SHIM, inp, tmp_path / "ours", k, [*flags, "--blocks-from", "3"])
+    ours, _ = _run_partitioned(SHIM, inp, tmp_path / "ours", k,
+                               [*flags, *merge, "--blocks-from", "3"])
     ref, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref", k, [*flags, "--blocks-from", "3"])
     for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
         assert _sha(ours + name) == _sha(ref + name), f"leg 1: {name} differs"
@@ -73,7 +78,7 @@ def test_resume_from_temp_file_bytes(tmp_path):
         os.makedirs(tmp_path / who)
         shutil.copy(ref + "tmp.vecs", str(tmp_path / who / "tmp.vecs"))
     more = [*flags, "--blocks-from", "6", "--no-init-temp-file"]
-    ours2, _ = _run_partitioned(SHIM, inp, tmp_path / "ours2", k, more)
+    ours2, _ = _run_partitioned(SHIM, inp, tmp_path / "ours2", k, [*more, *merge])
     ref2, _ = _run_partitioned(REF_CLI, inp, tmp_path / "ref2", k, more)
     for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
         assert _sha(ours2 + name) == _sha(ref2 + name), f"leg 2: {name} differs"

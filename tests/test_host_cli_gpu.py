@@ -152,6 +152,22 @@ def test_host_cli_resumes_from_temp_file(tmp_path):
         assert _sha(ours2 + name) == _sha(ref2 + name), f"leg 2: {name} differs"
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="host CLI not built")
+def test_host_merge_and_device_merge_write_the_same_bytes(tmp_path):
+    """The partitioned mode merges the blocks on the device by default (pqh_knn_heaps_*);
+    --host-merge keeps the heaps on the host, merged by the driver's own restatement of
+    fast_nn_heap_push.  Results, and the kept temp file, must not differ."""
+    x = make_golden.make_input("ties", 30000, 24, 3)
+    inp = str(tmp_path / "in.fvecs")
+    vecs_io.write_xvecs(inp, x, "f")
+    flags = ["--num-dims", "3", "--no-delete-temp-file"]
+    dev, out = _run_partitioned(CLI, inp, tmp_path / "dev", 14, flags)
+    host, _ = _run_partitioned(CLI, inp, tmp_path / "host", 14, [*flags, "--host-merge"])
+    for name in ("nn_indices.ivecsl", "nn_dist.fvecsl", "tmp.vecs"):
+        assert _sha(dev + name) == _sha(host + name), f"{name} differs"
+    assert "d2h 0.0 ms" in out or "d2h" in out
+
+
 def _n_devices():
     import torch
     return torch.cuda.device_count()

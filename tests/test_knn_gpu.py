@@ -188,14 +188,12 @@ def test_tensor_path_boundaries(oracle, n, d, k):
 
 
 KNOBS = [
-    dict(PQH_TC_EPI=16),
     dict(PQH_TC_MMA=2),
-    dict(PQH_TC_EPI=16, PQH_TC_MMA=2),
     dict(PQH_TC_ORDER=0),
-    dict(PQH_TC_ORDER=0, PQH_TC_EPI=16),
+    dict(PQH_TC_ORDER=0, PQH_TC_MMA=2),
     dict(PQH_TC_STREAM=1),
-    dict(PQH_TC_STREAM=1, PQH_TC_EPI=16),
-    dict(PQH_TC_I8=0, PQH_TC_EPI=16, PQH_TC_MMA=2),
+    dict(PQH_TC_STREAM=1, PQH_TC_ORDER=0),
+    dict(PQH_TC_I8=0, PQH_TC_MMA=2),
     dict(PQH_TC_SLICE_MB=64),
 ]
 
@@ -217,9 +215,9 @@ def _knob_cases(oracle):
 
 @pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a[7:]}={b}" for a, b in k.items()))
 def test_kernel_configurations_stay_exact(tc_env, oracle, knobs):
-    """Every selectable configuration of the tensor-core path -- 8 or 16 filter warps, one or two
-    MMA issuers, locality order on or off, the streaming kernel forced on a small d, small row
-    slices -- must produce the oracle's answer: the knobs only decide how fast."""
+    """Every selectable configuration of the tensor-core path -- one or two MMA issuers, locality
+    order on or off, the streaming kernel forced on a small d, small row slices -- must produce
+    the oracle's answer: the knobs only decide how fast."""
     c = _knob_cases(oracle)
     tc_env(**knobs)
     got = knn.knn_full_thread(c["x"], None, 17)
@@ -425,3 +423,54 @@ def test_integer_tensor_path(tc_env, oracle):
     z[17, 3] = -1.0
     assert_rows_equal(knn.knn_full_thread(z, None, 9), oracle.knn(z, None, 9))
     assert knn.last_stats()["inexact_operands"] in (0, 1)
+
+
+def test_device_side_merge_follows_the_reference_heap_rules(oracle):
+    """pqh_knn_heaps_* + pqh_knn_dataset_search_block_merge against a pure-Python restatement
+    of run_merge_block / fast_nn_heap_push / fast_nn_heap_sort (tests/ref_semantics.py, pinned
+    against the reference's compiled functions in test_oracle_pins.py): overlapping blocks with
+    duplicates and ties, a block smaller than k, a single-row block, a resumed image."""
+    from tests import ref_semantics as rs
+    n, d, k = 3000, 16, 6
+    x = synth.with_duplicates_and_ties(synth.sift_like(n, d, seed=21), n_dups=40, n_ties=40)
+    rng = np.random.default_rng(2)
+    blocks = [np.sort(rng.choice(n, m, replace=False)).astype(np.int32)
+              for m in (2600, 900, 4, 1, 2500, 700)]
+    heaps = [[[rs.UINT_MAX, np.float32(np.inf)] for _ in range(k)] for _ in range(n)]
+
+    def merge_host(ids):
+        m = len(ids)
+        k1 = min(k, m - 1) + 1
+        if m < 2:
+            return k1
+        ea, ed = oracle.knn(x[ids], None, k1)
+        for r in range(m):
+            for c in range(1, k1):
+                rs.heap_push(heaps[ids[r]], [int(ids[ea[r, c]]), np.float32(ed[r, c])], k)
+        return k1
+
+    knn.dataset_load(x)
+    try:
+        knn.heaps_create(n, k)
+        for t, ids in enumerate(blocks[:3]):
+            knn.dataset_search_block_merge(ids, merge_host(ids), t)
+        image, _, _ = knn.heaps_export(n, k)
+        exp = np.array([[tuple(it) for it in h] for h in heaps], dtype=knn.ITEM)
+        assert np.array_equal(image["id"], exp["id"])
+        assert np.array_equal(image["dist"].view(np.uint32), exp["dist"].view(np.uint32))
+        # resume from that image with the remaining blocks
+        knn.heaps_create(n, k, image)
+        for t, ids in enumerate(blocks[3:]):
+            knn.dataset_search_block_merge(ids, merge_host(ids), t)
+        image, ids_out, dists_out = knn.heaps_export(n, k)
+    finally:
+        knn.heaps_release()
+        knn.dataset_release()
+    exp = np.array([[tuple(it) for it in h] for h in heaps], dtype=knn.ITEM)
+    assert np.array_equal(image["id"], exp["id"])
+    assert np.array_equal(image["dist"].view(np.uint32), exp["dist"].view(np.uint32))
+    for r in rng.choice(n, 300, replace=False):
+        ei, ed = rs.heap_sort([list(it) for it in heaps[r]], k)
+        assert list(ids_out[r]) == [int(v) for v in ei]
+        assert np.array_equal(dists_out[r].view(np.uint32),
+                              np.array(ed, dtype=np.float32).view(np.uint32))

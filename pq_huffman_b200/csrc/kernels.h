@@ -49,15 +49,23 @@ struct OrderOut {
     const int *q_self;     // self-join: position of query r's own vector in the permuted base
     const int *qt_start;   // first base tile of the sweep of each query tile
 };
+struct OrderBufs {
+    int C;  // cells (= pivots); 0: no locality order
+    int *piv_ids, *cell_b, *base_perm, *base_inv, *cell_q, *q_perm, *q_self;
+    int *hist_b, *start_b, *cur_b, *hist_q, *start_q, *cur_q, *qt_start;
+};
 int order_num_cells(int nb);
 size_t order_workspace_bytes(int slice_rows, int nb, int slice_qtiles);
-cudaError_t launch_order_base(const float *d_base, int nb, int d, int slice_rows_max,
-                              int slice_qtiles_max, void *d_work, cudaStream_t stream,
-                              int *launches, OrderOut *out);
-cudaError_t launch_order_queries(const float *d_queries, int q_begin, int n_rows, int nb, int d,
-                                 int self_join, int n_qtiles, int slice_rows_max,
-                                 int slice_qtiles_max, void *d_work, cudaStream_t stream,
-                                 int *launches, OrderOut *out);
+void order_carve(void *d_work, int slice_rows, int nb, int slice_qtiles, OrderBufs *w);
+cudaError_t launch_order_pivots(const OrderBufs &w, int nb, cudaStream_t stream, int *launches);
+cudaError_t launch_order_pick(const void *cand, const int *cnt, int n_rows, int gcap, int nlists,
+                              int tail_row0, int ns_tail, int *cell, int *hist,
+                              cudaStream_t stream, int *launches);
+cudaError_t launch_order_sort_base(const OrderBufs &w, int nb, cudaStream_t stream, int *launches);
+cudaError_t launch_order_clear_queries(const OrderBufs &w, cudaStream_t stream);
+cudaError_t launch_order_sort_queries(const OrderBufs &w, int q_begin, int n_rows, int self_join,
+                                      int n_qtiles, cudaStream_t stream, int *launches,
+                                      OrderOut *out);
 cudaError_t launch_order_self_of(const int *d_ids, int n, const int *base_inv, int *d_q_self,
                                  cudaStream_t stream, int *launches);
 

@@ -4,18 +4,24 @@
 // score seen so far"; a base tile costs that row nothing once no score in it beats tau.  In the
 // order the caller's rows come in (compute_nn_fast.c:478-481 hands knn_full_thread whatever
 // order the .fvecs file has) near neighbours are spread over the whole base, tau tightens like
-// L/n along the sweep, and a third of all (warp, tile) pairs take the slow path.
+// L/n along the sweep, and a third of all (warp, tile) pairs take the slow path -- and because
+// an accumulator stage is only free again when all eight filter warps are done with it, one
+// slow warp stalls the whole tile.
 //
-// Here the base rows are grouped into cells of a coarse quantiser (nearest of C pivot rows,
-// measured on up to 32 sampled coordinates -- approximate on purpose, it only steers the
-// ORDER), the query rows of the launch are grouped the same way, and a query tile starts its
-// sweep at the cell its own rows belong to.  A row then meets most of its true neighbours in
-// the first few tiles and tau is tight for the rest of the sweep; the result is unchanged --
-// every row is still compared with every base row and certified as before -- only the order
-// in which the tiles are visited differs.  Candidate ids become positions in the permuted
-// base operand; the re-rank kernel maps them back (base_perm) before it orders ties.
+// Here the base rows are grouped into the cells of a coarse quantiser (nearest of C pivot rows),
+// the query rows of a launch are grouped the same way, and a query tile starts its sweep at the
+// cell its own rows belong to.  A row then meets most of its true neighbours in the first few
+// tiles and tau is tight for the rest of the sweep (measured on SIFT1M-shaped data, 4096 cells:
+// slow (warp, tile) pairs 33 % -> 0.6 %).  The result is unchanged -- every row is still
+// compared with every base row and certified as before -- only the order in which the tiles
+// are visited differs.  Candidate ids become positions in the permuted base operand; the
+// re-rank kernel maps them back (base_perm) before it orders ties.
 //
-// Cost: n x C x 32 FMAs + three passes over n integers (1M x 128: 1024 cells, < 2 ms).
+// The nearest pivot of a row is itself a k = 1 search of the row against the C pivots, so it
+// runs on the tensor cores through the same GEMM + filter kernel (launch_knn_tc drives it:
+// pivot operand, one short sweep per row slice, then order_pick_kernel takes the best entry of
+// every row's candidate list); what is here are the small integer kernels around it: pivot
+// choice, counting sort by cell, inverse permutation, start tile of every query tile.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -25,72 +31,37 @@ namespace pqh {
 
 namespace {
 
-constexpr int ORD_DSUB = 128;      // coordinates used for the cell assignment (sampled if d is larger)
-constexpr int ORD_PCHUNK = 64;     // pivots per shared-memory chunk
 constexpr int ORD_MAX_CELLS = 4096;
+constexpr int ORD_MIN_CELLS = 512;  // four base tiles: the shortest sweep the filter kernel takes
 
-// pivot c = base row (c + 1/2) * nb / C, restricted to the sampled coordinates; pn[c] = |p|^2
-__global__ void order_pivots_kernel(const float *__restrict__ base, int nb, int d, int dsub,
-                                    int C, float *__restrict__ piv, float *__restrict__ pn) {
+// pivot c = base row (c + 1/2) * nb / C
+__global__ void order_pivot_ids_kernel(int *__restrict__ ids, int C, int nb) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const size_t row = (size_t)(((long long)c * 2 + 1) * nb / (2LL * C));
-    float s = 0.0f;
-    for (int j = 0; j < ORD_DSUB; ++j) {
-        float v = 0.0f;
-        if (j < dsub) v = base[row * d + (size_t)((long long)j * d / dsub)];
-        piv[(size_t)c * ORD_DSUB + j] = v;
-        s += v * v;
-    }
-    pn[c] = s;
+    if (c < C) ids[c] = (int)(((long long)c * 2 + 1) * nb / (2LL * C));
 }
 
-// cell[i] = argmin_c |x_i - p_c|^2 over the sampled coordinates (= argmin |p|^2 - 2 x.p);
-// hist[cell]++.  One thread per row, the pivots streamed through shared memory.
-__global__ void __launch_bounds__(128)
-order_assign_kernel(const float *__restrict__ x, int n, int d, int dsub, int C,
-                    const float *__restrict__ piv, const float *__restrict__ pn,
-                    int *__restrict__ cell, int *__restrict__ hist) {
-    __shared__ __align__(16) float sp[ORD_PCHUNK * ORD_DSUB];
-    __shared__ float sn[ORD_PCHUNK];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float xv[ORD_DSUB];
-#pragma unroll
-    for (int j = 0; j < ORD_DSUB; ++j) {
-        xv[j] = 0.0f;
-        if (i < n && j < dsub) xv[j] = __ldg(x + (size_t)i * d + (size_t)((long long)j * d / dsub));
-    }
-    float best = __int_as_float(0x7f800000);
-    int bc = 0;
-    for (int c0 = 0; c0 < C; c0 += ORD_PCHUNK) {
-        __syncthreads();
-        const int nc = C - c0 < ORD_PCHUNK ? C - c0 : ORD_PCHUNK;
-        for (int t = threadIdx.x; t < nc * ORD_DSUB; t += blockDim.x)
-            sp[t] = piv[(size_t)c0 * ORD_DSUB + t];
-        for (int t = threadIdx.x; t < nc; t += blockDim.x) sn[t] = pn[c0 + t];
-        __syncthreads();
-        for (int c = 0; c < nc; ++c) {
-            const float4 *p4 = reinterpret_cast<const float4 *>(sp + c * ORD_DSUB);
-            float dot = 0.0f;
-#pragma unroll
-            for (int j = 0; j < ORD_DSUB / 4; ++j) {
-                const float4 p = p4[j];
-                dot = fmaf(xv[4 * j + 0], p.x, dot);
-                dot = fmaf(xv[4 * j + 1], p.y, dot);
-                dot = fmaf(xv[4 * j + 2], p.z, dot);
-                dot = fmaf(xv[4 * j + 3], p.w, dot);
-            }
-            const float s = fmaf(-2.0f, dot, sn[c]);
-            if (s < best) {
-                best = s;
-                bc = c0 + c;
-            }
+// cell[r] = position (= pivot number) of the best-scoring entry of row r's candidate lists from
+// the sweep over the pivots; hist[cell]++.  Keys order by descending score, so the smallest key
+// of a row is its nearest pivot.
+__global__ void order_pick_kernel(const key64_t *__restrict__ cand, const int *__restrict__ cnt,
+                                  int n_rows, int gcap, int nlists, int tail_row0, int ns_tail,
+                                  int *__restrict__ cell, int *__restrict__ hist) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int my_lists = r < tail_row0 ? nlists : ns_tail;
+    const size_t slot0 = list_slot(r, 0, tail_row0, nlists, ns_tail);
+    key64_t best = KEY_INF;
+    for (int s = 0; s < my_lists; ++s) {
+        const key64_t *l = cand + (slot0 + s) * gcap;
+        const int c = cnt[slot0 + s];
+        for (int i = 0; i < c; ++i) {
+            const key64_t k = __ldcg(l + i);
+            best = k < best ? k : best;
         }
     }
-    if (i < n) {
-        cell[i] = bc;
-        atomicAdd(hist + bc, 1);
-    }
+    const int c = best == KEY_INF ? 0 : (int)(uint32_t)best;
+    cell[r] = c;
+    atomicAdd(hist + c, 1);
 }
 
 // the query rows of a self-join share the base rows' cells: only count them
@@ -170,120 +141,107 @@ size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
+// 0: no locality order for a base this small (the sweep is too short to matter)
 int order_num_cells(int nb) {
     static const int forced = [] {
         const char *e = getenv("PQH_TC_CELLS");  // experiments
         return e ? atoi(e) : 0;
     }();
-    if (forced >= 16 && forced <= ORD_MAX_CELLS) return forced;
-    int c = 16;
-    while (c < ORD_MAX_CELLS && (long long)c * 1024 < nb) c *= 2;
+    if (nb < 32768) return 0;
+    if (forced >= ORD_MIN_CELLS && forced <= ORD_MAX_CELLS) return forced / TC_BN * TC_BN;
+    int c = ORD_MIN_CELLS;
+    while (c < ORD_MAX_CELLS && (long long)c * 256 < nb) c *= 2;
     return c;
 }
 
 size_t order_workspace_bytes(int slice_rows, int nb, int slice_qtiles) {
     const int C = order_num_cells(nb);
     size_t b = 0;
-    b += up256((size_t)C * ORD_DSUB * sizeof(float)) + up256((size_t)C * sizeof(float));  // pivots
+    b += up256((size_t)C * sizeof(int));               // pivot ids
     b += 3 * up256((size_t)nb * sizeof(int));          // cell_b, base_perm, base_inv
     b += 3 * up256((size_t)slice_rows * sizeof(int));  // cell_q, q_perm, q_self
-    b += 5 * up256((size_t)(C + 1) * sizeof(int));     // hist_b, start_b, cur_b | hist_q, start_q
-    b += up256((size_t)(C + 1) * sizeof(int));         // cur_q
+    b += 6 * up256((size_t)(C + 1) * sizeof(int));     // hist / start / cursor, base and queries
     b += up256((size_t)slice_qtiles * sizeof(int));
     return b + 256;
 }
 
-namespace {
-struct OrderWork {
-    int C, dsub;
-    float *piv, *pn;
-    int *cell_b, *base_perm, *base_inv, *cell_q, *q_perm, *q_self;
-    int *hist_b, *start_b, *cur_b, *hist_q, *start_q, *cur_q, *qt_start;
-};
-OrderWork carve(void *d_work, int slice_rows, int nb, int d, int slice_qtiles) {
-    OrderWork w;
-    w.C = order_num_cells(nb);
-    static const int forced_dims = [] {
-        const char *e = getenv("PQH_TC_ODIMS");  // experiments
-        return e ? atoi(e) : 0;
-    }();
-    w.dsub = d < ORD_DSUB ? d : ORD_DSUB;
-    if (forced_dims >= 1 && forced_dims < w.dsub) w.dsub = forced_dims;
+void order_carve(void *d_work, int slice_rows, int nb, int slice_qtiles, OrderBufs *w) {
+    w->C = order_num_cells(nb);
     unsigned char *p = reinterpret_cast<unsigned char *>(((uintptr_t)d_work + 255) & ~(uintptr_t)255);
     auto take = [&](size_t bytes) {
         void *r = p;
         p += up256(bytes);
         return r;
     };
-    w.piv = static_cast<float *>(take((size_t)w.C * ORD_DSUB * sizeof(float)));
-    w.pn = static_cast<float *>(take((size_t)w.C * sizeof(float)));
-    w.cell_b = static_cast<int *>(take((size_t)nb * sizeof(int)));
-    w.base_perm = static_cast<int *>(take((size_t)nb * sizeof(int)));
-    w.base_inv = static_cast<int *>(take((size_t)nb * sizeof(int)));
-    w.cell_q = static_cast<int *>(take((size_t)slice_rows * sizeof(int)));
-    w.q_perm = static_cast<int *>(take((size_t)slice_rows * sizeof(int)));
-    w.q_self = static_cast<int *>(take((size_t)slice_rows * sizeof(int)));
-    w.hist_b = static_cast<int *>(take((size_t)(w.C + 1) * sizeof(int)));
-    w.start_b = static_cast<int *>(take((size_t)(w.C + 1) * sizeof(int)));
-    w.cur_b = static_cast<int *>(take((size_t)(w.C + 1) * sizeof(int)));
-    w.hist_q = static_cast<int *>(take((size_t)(w.C + 1) * sizeof(int)));
-    w.start_q = static_cast<int *>(take((size_t)(w.C + 1) * sizeof(int)));
-    w.cur_q = static_cast<int *>(take((size_t)(w.C + 1) * sizeof(int)));
-    w.qt_start = static_cast<int *>(take((size_t)slice_qtiles * sizeof(int)));
-    return w;
+    w->piv_ids = static_cast<int *>(take((size_t)w->C * sizeof(int)));
+    w->cell_b = static_cast<int *>(take((size_t)nb * sizeof(int)));
+    w->base_perm = static_cast<int *>(take((size_t)nb * sizeof(int)));
+    w->base_inv = static_cast<int *>(take((size_t)nb * sizeof(int)));
+    w->cell_q = static_cast<int *>(take((size_t)slice_rows * sizeof(int)));
+    w->q_perm = static_cast<int *>(take((size_t)slice_rows * sizeof(int)));
+    w->q_self = static_cast<int *>(take((size_t)slice_rows * sizeof(int)));
+    w->hist_b = static_cast<int *>(take((size_t)(w->C + 1) * sizeof(int)));
+    w->start_b = static_cast<int *>(take((size_t)(w->C + 1) * sizeof(int)));
+    w->cur_b = static_cast<int *>(take((size_t)(w->C + 1) * sizeof(int)));
+    w->hist_q = static_cast<int *>(take((size_t)(w->C + 1) * sizeof(int)));
+    w->start_q = static_cast<int *>(take((size_t)(w->C + 1) * sizeof(int)));
+    w->cur_q = static_cast<int *>(take((size_t)(w->C + 1) * sizeof(int)));
+    w->qt_start = static_cast<int *>(take((size_t)slice_qtiles * sizeof(int)));
 }
-}  // namespace
 
-// Once per search: cells of the base rows, the permuted base order and its inverse.
-cudaError_t launch_order_base(const float *d_base, int nb, int d, int slice_rows_max,
-                              int slice_qtiles_max, void *d_work, cudaStream_t stream,
-                              int *launches, OrderOut *out) {
-    const OrderWork w = carve(d_work, slice_rows_max, nb, d, slice_qtiles_max);
-    cudaError_t e;
-    // hist_b, start_b, cur_b are contiguous: one memset
-    if ((e = cudaMemsetAsync(w.hist_b, 0, 3 * up256((size_t)(w.C + 1) * sizeof(int)), stream)) !=
-        cudaSuccess)
-        return e;
-    order_pivots_kernel<<<(w.C + 127) / 128, 128, 0, stream>>>(d_base, nb, d, w.dsub, w.C, w.piv,
-                                                               w.pn);
-    order_assign_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d_base, nb, d, w.dsub, w.C, w.piv,
-                                                              w.pn, w.cell_b, w.hist_b);
-    order_scan_kernel<<<1, 1024, 0, stream>>>(w.hist_b, w.C, w.start_b, w.cur_b);
-    order_scatter_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(w.cell_b, nb, 0, w.cur_b,
-                                                               w.base_perm, w.base_inv);
-    *launches += 4;
-    out->base_perm = w.base_perm;
-    out->base_inv = w.base_inv;
-    out->q_perm = nullptr;
-    out->q_self = nullptr;
-    out->qt_start = nullptr;
+// pivot rows; clears the base histogram
+cudaError_t launch_order_pivots(const OrderBufs &w, int nb, cudaStream_t stream, int *launches) {
+    cudaError_t e = cudaMemsetAsync(w.hist_b, 0, 3 * up256((size_t)(w.C + 1) * sizeof(int)), stream);
+    if (e != cudaSuccess) return e;
+    order_pivot_ids_kernel<<<(w.C + 127) / 128, 128, 0, stream>>>(w.piv_ids, w.C, nb);
+    ++*launches;
     return cudaGetLastError();
 }
 
+// cells of the rows of one assignment sweep, from its candidate lists
+cudaError_t launch_order_pick(const void *cand, const int *cnt, int n_rows, int gcap, int nlists,
+                              int tail_row0, int ns_tail, int *cell, int *hist,
+                              cudaStream_t stream, int *launches) {
+    order_pick_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(
+        static_cast<const key64_t *>(cand), cnt, n_rows, gcap, nlists, tail_row0, ns_tail, cell,
+        hist);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// Once per search, after every base row has its cell: the permuted base order and its inverse.
+cudaError_t launch_order_sort_base(const OrderBufs &w, int nb, cudaStream_t stream, int *launches) {
+    order_scan_kernel<<<1, 1024, 0, stream>>>(w.hist_b, w.C, w.start_b, w.cur_b);
+    order_scatter_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(w.cell_b, nb, 0, w.cur_b,
+                                                               w.base_perm, w.base_inv);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+// clears the query histogram of a slice (before launch_order_pick fills it for queries that are
+// not base rows)
+cudaError_t launch_order_clear_queries(const OrderBufs &w, cudaStream_t stream) {
+    return cudaMemsetAsync(w.hist_q, 0, 3 * up256((size_t)(w.C + 1) * sizeof(int)), stream);
+}
+
 // Once per row slice: the slice's query rows [q_begin, q_begin + n_rows) grouped by cell.
-// d_queries: the FP32 rows of the slice (row r is query q_begin + r) when they are not base
-// rows; null for a self-join (query q is base row q).
-cudaError_t launch_order_queries(const float *d_queries, int q_begin, int n_rows, int nb, int d,
-                                 int self_join, int n_qtiles, int slice_rows_max,
-                                 int slice_qtiles_max, void *d_work, cudaStream_t stream,
-                                 int *launches, OrderOut *out) {
-    const OrderWork w = carve(d_work, slice_rows_max, nb, d, slice_qtiles_max);
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(w.hist_q, 0, 3 * up256((size_t)(w.C + 1) * sizeof(int)), stream)) !=
-        cudaSuccess)
-        return e;
+// Self-join: query q is base row q and shares its cell; otherwise cell_q / hist_q were filled by
+// launch_order_pick.
+cudaError_t launch_order_sort_queries(const OrderBufs &w, int q_begin, int n_rows, int self_join,
+                                      int n_qtiles, cudaStream_t stream, int *launches,
+                                      OrderOut *out) {
     const int *cq = w.cell_q;
     if (self_join) {
+        cudaError_t e = launch_order_clear_queries(w, stream);
+        if (e != cudaSuccess) return e;
         cq = w.cell_b + q_begin;
         order_count_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(cq, n_rows, w.hist_q);
-    } else {
-        order_assign_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(
-            d_queries, n_rows, d, w.dsub, w.C, w.piv, w.pn, w.cell_q, w.hist_q);
+        ++*launches;
     }
     order_scan_kernel<<<1, 1024, 0, stream>>>(w.hist_q, w.C, w.start_q, w.cur_q);
     order_scatter_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(cq, n_rows, q_begin, w.cur_q,
                                                                    w.q_perm, nullptr);
-    *launches += 3;
+    *launches += 2;
     if (self_join) {
         order_qself_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(w.q_perm, n_rows, w.base_inv,
                                                                      w.q_self);

@@ -54,6 +54,7 @@ struct TcEnv {
     int order = 1;     // PQH_TC_ORDER: locality order of the sweep (knn_order.cu)
     int nmma = 1;      // PQH_TC_MMA: MMA-issuing threads per CTA, 1 or 2
     int early = 0;     // PQH_TC_EARLY: release the accumulator stage before filtering
+    int spin = 0;      // PQH_TC_SPIN: poll the accumulator barriers instead of suspending
     int l_exact = 0, l_inexact = 0;  // PQH_TC_LEXACT / PQH_TC_LINEXACT: candidates kept per row
     int gcap = 0;      // PQH_TC_GCAP: list capacity, 256 or 512
     int nsplit = 0;    // PQH_TC_NSPLIT: base splits
@@ -171,7 +172,8 @@ __global__ void fold_const_kernel(__half *__restrict__ fa) {
 // Integer path, one warp per operand row: the row as 8-bit integers -- u8 x for the A (query)
 // operand, s8 x - 128 for the B (base) operand -- zero-padded to d32 bytes; FP64 squared norm
 // (stored under the data row); for base rows the 32 s8 fold digits of G = ceil(|y|^2 / 2).
-// sc->i8_reject collects the reasons the integer path cannot be used.  out == null: only check.
+// sc->i8_reject collects the reasons the integer path cannot be used.  out == fold == null: only
+// check.
 __global__ void __launch_bounds__(256)
 prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t *__restrict__ out,
                     double *__restrict__ norm64, int8_t *__restrict__ fold, int as_base,
@@ -196,7 +198,7 @@ prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t 
     for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
     unsigned flags = __any_sync(0xffffffffu, bad) ? 1u : 0u;
     if (norm64 && lane == 0) norm64[src] = acc;
-    if (fold) {
+    if (as_base) {
         const long long G = ((long long)acc + 1) / 2;
         const long long q = G / I8_FOLD_UNIT;
         const int r = (int)(G % I8_FOLD_UNIT);
@@ -209,7 +211,7 @@ prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t 
             const int r2 = r % 255, first = r2 < 127 ? r2 : 127;
             b = lane == I8_FOLD_FULL ? -first : -(r2 - first);
         }
-        fold[(size_t)row * 32 + lane] = (int8_t)b;
+        if (fold) fold[(size_t)row * 32 + lane] = (int8_t)b;
     }
     if (flags && lane == 0) atomicOr(&sc->i8_reject, flags);
 }
@@ -230,7 +232,13 @@ struct TcSmemTail {
 };
 
 // both barriers of an MMA step probed together: their latencies overlap instead of adding up
-__device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *b1, uint32_t p1) {
+__device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *b1, uint32_t p1,
+                                           bool spin) {
+    if (spin) {
+        ptx::mbar_spin(b0, p0);
+        ptx::mbar_spin(b1, p1);
+        return;
+    }
     const bool ok0 = ptx::mbar_try_wait(b0, p0);
     const bool ok1 = ptx::mbar_try_wait(b1, p1);
     if (!ok0) ptx::mbar_wait_slow(b0, p0);
@@ -353,7 +361,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     const int stage = (int)(s % TC_NSTAGE), as = (int)(s & 1u);
                     const uint32_t ph = (s / TC_NSTAGE) & 1u, acc_ph = (s >> 1) & 1u;
                     const long long w0 = prof ? clock64() : 0;
-                    mbar_wait2(&tail.b_full[stage], ph, &tail.eb.acc_empty[as], acc_ph ^ 1);
+                    mbar_wait2(&tail.b_full[stage], ph, &tail.eb.acc_empty[as], acc_ph ^ 1,
+                               args.spin != 0);
                     if (prof) t_wait += clock64() - w0;
                     ptx::tc_fence_after_sync();
                     const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
@@ -688,11 +697,13 @@ int pick_L(int kcap, bool inexact) {
     if (L < 64) L = 64;
     return L;
 }
-// list capacity: the filter checks it once per tile, after up to TC_BN (128) appends
+// List capacity.  The filter checks the count once per tile, after up to TC_BN (128) appends,
+// and a shrink leaves up to L + L/2 entries: L + L/2 + TC_BN must fit.
 int pick_gcap(int L) {
+    const int need = L + L / 2 + TC_BN;
     const int e = env().gcap;
-    if ((e == 256 || e == 512) && L <= 96) return e;
-    return L <= 96 ? 256 : 512;
+    if ((e == 256 || e == 512) && need <= e) return e;
+    return need <= 256 ? 256 : 512;
 }
 
 size_t tc_smem_bytes(const TcPlan &p) {
@@ -763,6 +774,8 @@ struct TcLayout {
     bool streaming, order;
     int slice_rows, slice_qtiles;
     size_t scalars, xh_b, fold_b, fold_a, norm_b, norm_q, xq, cand, cnt, tau, fb_rows, order_ws;
+    size_t piv_op, piv_fold;  // locality order: operand rows and fold pieces of the pivots
+    int cells;
     // second pass (rows that failed the first certificate, redone with longer lists)
     size_t p2_q, p2_xh, p2_norm, p2_cand, p2_cnt, p2_tau, p2_fb, p2_self;
     int p2_rows;  // rows per second-pass batch
@@ -779,7 +792,8 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     lo->gcap = pick_gcap(lo->L);
     lo->streaming = ev.streaming || !resident_fits(lo->d16);
     lo->nmma = lo->streaming ? 1 : ev.nmma;
-    lo->order = ev.order && nb >= 8192;
+    lo->cells = ev.order ? order_num_cells(nb) : 0;
+    lo->order = lo->cells > 0;
     lo->n_btiles = (nb + TC_BN - 1) / TC_BN;
     // row slice: as many whole rounds of the grid as the list budget allows
     {
@@ -823,6 +837,8 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     lo->tau = take(n_lists * sizeof(float));
     lo->fb_rows = take((size_t)n_rows * sizeof(int));
     lo->order_ws = lo->order ? take(order_workspace_bytes(lo->slice_rows, nb, lo->slice_qtiles)) : 0;
+    lo->piv_op = lo->order ? take((size_t)lo->cells * lo->d16 * sizeof(__half)) : 0;
+    lo->piv_fold = lo->order ? take((size_t)lo->cells * FOLD_COLS * sizeof(__half)) : 0;
     {
         int p2 = n_rows / 16;
         if (p2 < 2048) p2 = 2048;
@@ -868,6 +884,7 @@ void tc_reload_env() {
     e.order = env_int("PQH_TC_ORDER", 1) != 0;
     e.nmma = env_int("PQH_TC_MMA", 1) == 2 ? 2 : 1;
     e.early = env_int("PQH_TC_EARLY", 0) != 0;
+    e.spin = env_int("PQH_TC_SPIN", 0) != 0;
     e.l_exact = env_int("PQH_TC_LEXACT", 0);
     e.l_inexact = env_int("PQH_TC_LINEXACT", 0);
     e.gcap = env_int("PQH_TC_GCAP", 0);
@@ -955,33 +972,21 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     const float *q_mat = self_join ? d_base : d_queries;
     const int q_src0 = self_join ? q_begin : q_begin - q_row0;
 
-    // ---- locality order of the base (once per search) ----
-    OrderOut oo = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (lo.order) {
-        if ((e = launch_order_base(d_base, nb, d, lo.slice_rows, lo.slice_qtiles, order_ws, stream,
-                                   launches, &oo)) != cudaSuccess)
-            return e;
-    }
-    const int *base_perm = oo.base_perm;
-
-    // ---- base operand, integer flavour: tried first, kept only if every value qualifies ----
+    // ---- which operand flavour does the data allow?  Integers in [0, 255] whose norms fit the
+    //      fold columns take the exact INT8 path; one flag read-back decides ----
     bool used_i8 = false;
     const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode == 0 || debug_mode == 1) &&
                              resident_fits(lo.d32 / 2);
     if (i8_possible) {
-        prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(
-            d_base, nb, d, lo.d32, reinterpret_cast<uint8_t *>(xh_b), norm_b,
-            reinterpret_cast<int8_t *>(fold_b), 1, base_perm, 0, sc);
+        prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d32, nullptr,
+                                                              nullptr, nullptr, 1, nullptr, 0, sc);
         ++*launches;
-        if (!self_join) {  // the queries must qualify too: check them all, build nothing yet
+        if (!self_join) {
             prep_rows_i8_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(
                 q_mat + (size_t)q_src0 * d, n_rows, d, lo.d32, nullptr, nullptr, nullptr, 0,
                 nullptr, 0, sc);
             ++*launches;
         }
-        fold_const_i8_kernel<<<(TC_ROWS * 32 + 255) / 256, 256, 0, stream>>>(
-            reinterpret_cast<uint8_t *>(fold_a));
-        ++*launches;
         PrepScalars probe;
         if ((e = cudaMemcpyAsync(&probe, sc, sizeof(PrepScalars), cudaMemcpyDeviceToHost,
                                  stream)) != cudaSuccess)
@@ -989,9 +994,8 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
         used_i8 = probe.i8_reject == 0;
     }
-
-    // ---- base operand, FP16 flavour ----
-    auto prep_base_fp16 = [&]() {
+    // FP16 flavour: the common scale of all operands
+    auto prep_scale_fp16 = [&]() {
         const int grid_ma = num_sms * 8;
         maxabs_kernel<<<grid_ma, 256, 0, stream>>>(d_base, (size_t)nb * d, &sc->maxabs_bits);
         ++*launches;
@@ -1000,22 +1004,41 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                                                        (size_t)n_rows * d, &sc->maxabs_bits);
             ++*launches;
         }
-        prep_rows_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d16, xh_b, norm_b,
-                                                           fold_b, 1, base_perm, 0, sc);
-        fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
-        *launches += 2;
     };
-    if (!used_i8) prep_base_fp16();
-    if (times) cudaEventRecord(evs[1], stream);
+    if (!used_i8) prep_scale_fp16();
+    if (used_i8)
+        fold_const_i8_kernel<<<(TC_ROWS * 32 + 255) / 256, 256, 0, stream>>>(
+            reinterpret_cast<uint8_t *>(fold_a));
+    else
+        fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
+    ++*launches;
+    // operand rows of a set of data rows (perm: operand row p is data row perm[p] - perm_off)
+    auto prep_rows = [&](bool i8, const float *src, int n, void *op, double *norms, void *fold,
+                         bool as_base, const int *perm, int perm_off) {
+        if (i8)
+            prep_rows_i8_kernel<<<(n + 7) / 8, 256, 0, stream>>>(
+                src, n, d, lo.d32, static_cast<uint8_t *>(op), norms, static_cast<int8_t *>(fold),
+                as_base ? 1 : 0, perm, perm_off, sc);
+        else
+            prep_rows_kernel<<<(n + 7) / 8, 256, 0, stream>>>(
+                src, n, d, lo.d16, static_cast<__half *>(op), norms, static_cast<__half *>(fold),
+                as_base ? 1 : 0, perm, perm_off, sc);
+        ++*launches;
+    };
 
-    // ---- one pass = tensor-core kernel + re-rank over a set of query rows ----
+    const int *base_perm = nullptr;  // set once the locality order of the base exists
+
+    // ---- one pass = tensor-core kernel + (re-rank | cell pick) over a set of query rows ----
     struct Pass {
         TcGeom g;
-        int L_exact, L_inexact, gcap, nmma;
+        int L_exact, L_inexact, gcap, nmma, kcap, self_join;
         bool streaming;
         const void *a_op;        // query operand: row (q_op_begin + r) is query row r
         uint64_t a_rows;         // rows of that operand
         int q_op_begin;
+        const void *b_op;        // base operand and its fold pieces (nb_rows rows)
+        const void *b_fold;
+        int nb_rows, n_btiles;
         const float *queries;    // FP32 rows of the pass's queries (see RerankArgs)
         const double *qnorm64;   // indexed like `queries`
         int q_begin;             // absolute query id of row 0 (natural order) / of queries[0]
@@ -1026,9 +1049,11 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         float *tau;
         int *fb_rows;
         uint32_t *fb_count;
-        bool i8;                 // integer operands (first pass only)
+        bool i8;                 // integer operands
         int op_cols;             // operand row length in 2-byte units (the tensor maps' view)
         cudaEvent_t *ev3;        // gemm start / gemm end / re-rank end, or null
+        int *pick_cell, *pick_hist;  // locality order: take each row's nearest pivot instead of
+                                     // re-ranking (the base operand is the pivot set)
     };
     auto run_pass = [&](const Pass &p) -> cudaError_t {
         TcMaps maps;
@@ -1039,18 +1064,18 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             // classes a small d never uses still need a legal box
             const uint32_t bc = boxc[c] <= (uint32_t)p.op_cols ? boxc[c] : 16;
             if (!make_map(&maps.a[c], p.a_op, p.a_rows, p.op_cols, bc, TC_ROWS) ||
-                !make_map(&maps.b[c], xh_b, nb, p.op_cols, bc, TC_BN))
+                !make_map(&maps.b[c], p.b_op, p.nb_rows, p.op_cols, bc, TC_BN))
                 return cudaErrorInvalidValue;
         }
         if (!make_map(&maps.fa, fold_a, TC_ROWS, FOLD_COLS, FOLD_COLS, TC_ROWS) ||
-            !make_map(&maps.fb, fold_b, nb, FOLD_COLS, FOLD_COLS, TC_BN))
+            !make_map(&maps.fb, p.b_fold, p.nb_rows, FOLD_COLS, FOLD_COLS, TC_BN))
             return cudaErrorInvalidValue;
 
         args.n_rows = p.n_rows;
         args.q_begin = p.q_begin;
         args.q_op_begin = p.q_op_begin;
-        args.nb = nb;
-        args.self_join = self_join;
+        args.nb = p.nb_rows;
+        args.self_join = p.self_join;
         args.row_ids = p.row_ids;
         args.q_self = p.q_self;
         args.qt_start = p.qt_start;
@@ -1060,9 +1085,10 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         args.ns_tail = p.g.ns_tail;
         args.tiles_per_split_tail = p.g.tiles_per_split_tail;
         args.tiles_per_split = p.g.tiles_per_split;
-        args.n_btiles = lo.n_btiles;
-        args.debug_mode = debug_mode;
-        args.kcap = kcap;
+        args.n_btiles = p.n_btiles;
+        args.debug_mode = p.pick_cell ? 0 : debug_mode;
+        args.spin = ev.spin;
+        args.kcap = p.kcap;
         args.L_exact = p.L_exact;
         args.L_inexact = p.L_inexact;
         args.sc = sc;
@@ -1082,15 +1108,23 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             const int grid = n_items < num_sms ? n_items : num_sms;
             const size_t smem = tc_smem_bytes(args.plan);
             if (p.i8)
-                pe = p.gcap == 256 ? launch_tc_cfg<256, true>(maps, args, smem, grid, p.nmma, ev.early != 0, stream)
-                                   : launch_tc_cfg<512, true>(maps, args, smem, grid, p.nmma, ev.early != 0, stream);
+                pe = p.gcap == 256 ? launch_tc_cfg<256, true>(maps, args, smem, grid, p.nmma,
+                                                               ev.early != 0, stream)
+                                   : launch_tc_cfg<512, true>(maps, args, smem, grid, p.nmma,
+                                                               ev.early != 0, stream);
             else
-                pe = p.gcap == 256 ? launch_tc_cfg<256, false>(maps, args, smem, grid, p.nmma, ev.early != 0, stream)
-                                   : launch_tc_cfg<512, false>(maps, args, smem, grid, p.nmma, ev.early != 0, stream);
+                pe = p.gcap == 256 ? launch_tc_cfg<256, false>(maps, args, smem, grid, p.nmma,
+                                                                ev.early != 0, stream)
+                                   : launch_tc_cfg<512, false>(maps, args, smem, grid, p.nmma,
+                                                                ev.early != 0, stream);
             if (pe != cudaSuccess) return pe;
         }
         ++*launches;
         if (p.ev3) cudaEventRecord(p.ev3[1], stream);
+        if (p.pick_cell)
+            return launch_order_pick(p.cand, p.cnt, p.n_rows, p.gcap, p.g.nsplit,
+                                     p.g.q_tail0 * TC_ROWS, p.g.ns_tail, p.pick_cell, p.pick_hist,
+                                     stream, launches);
 
         // ---- re-rank + certificate ----
         RerankArgs ra;
@@ -1147,6 +1181,68 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         return cudaGetLastError();
     };
 
+    // ---- locality order: the nearest pivot of every row is a k = 1 sweep of the rows against
+    //      the pivot set on the tensor cores; its candidate lists give the cells ----
+    OrderBufs ob;
+    ob.C = 0;
+    OrderOut oo = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *piv_op = w + lo.piv_op, *piv_fold = w + lo.piv_fold;
+    // cells of `n` rows of `src` (row i of src) into cell_out / hist, slice by slice
+    auto assign_cells = [&](const float *src, int n, int *cell_out, int *hist) -> cudaError_t {
+        for (int r0 = 0; r0 < n; r0 += lo.slice_rows) {
+            const int rows = n - r0 < lo.slice_rows ? n - r0 : lo.slice_rows;
+            prep_rows(used_i8, src + (size_t)r0 * d, rows, xq, nullptr, nullptr, false, nullptr, 0);
+            Pass pa;
+            tc_geom(rows, lo.cells / TC_BN, lo.gcap, num_sms, &pa.g);
+            pa.L_exact = pa.L_inexact = 8;
+            pa.gcap = lo.gcap;
+            pa.nmma = lo.nmma;
+            pa.kcap = 1;
+            pa.self_join = 0;
+            pa.streaming = lo.streaming;
+            pa.a_op = xq;
+            pa.a_rows = (uint64_t)rows;
+            pa.q_op_begin = 0;
+            pa.b_op = piv_op;
+            pa.b_fold = piv_fold;
+            pa.nb_rows = lo.cells;
+            pa.n_btiles = lo.cells / TC_BN;
+            pa.queries = nullptr;
+            pa.qnorm64 = nullptr;
+            pa.q_begin = 0;
+            pa.row_ids = pa.q_perm = pa.q_self = pa.qt_start = nullptr;
+            pa.n_rows = rows;
+            pa.cand = cand;
+            pa.cnt = cnt;
+            pa.tau = tau;
+            pa.fb_rows = nullptr;
+            pa.fb_count = nullptr;
+            pa.i8 = used_i8;
+            pa.op_cols = used_i8 ? lo.d32 / 2 : lo.d16;
+            pa.ev3 = nullptr;
+            pa.pick_cell = cell_out + r0;
+            pa.pick_hist = hist;
+            cudaError_t pe = run_pass(pa);
+            if (pe != cudaSuccess) return pe;
+        }
+        return cudaSuccess;
+    };
+    if (lo.order) {
+        order_carve(order_ws, lo.slice_rows, nb, lo.slice_qtiles, &ob);
+        if ((e = launch_order_pivots(ob, nb, stream, launches)) != cudaSuccess) return e;
+        prep_rows(used_i8, d_base, ob.C, piv_op, nullptr, piv_fold, true, ob.piv_ids, 0);
+        if ((e = assign_cells(d_base, nb, ob.cell_b, ob.hist_b)) != cudaSuccess) return e;
+        if ((e = launch_order_sort_base(ob, nb, stream, launches)) != cudaSuccess) return e;
+        base_perm = ob.base_perm;
+    }
+
+    // ---- base operand (rows in cell order when the locality order is on) ----
+    auto prep_base = [&](bool i8) {
+        prep_rows(i8, d_base, nb, xh_b, norm_b, fold_b, true, base_perm, 0);
+    };
+    prep_base(used_i8);
+    if (times) cudaEventRecord(evs[1], stream);
+
     // ---- first pass: the rows of this call, slice by slice ----
     for (int si = 0; si < n_slices; ++si) {
         const int s_begin = q_begin + si * lo.slice_rows;  // absolute id of the slice's row 0
@@ -1158,39 +1254,37 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         Pass p1;
         tc_geom(rows, lo.n_btiles, lo.gcap, num_sms, &p1.g);
         if (lo.order) {
-            if ((e = launch_order_queries(self_join ? nullptr : q_slice, s_begin, rows, nb, d,
-                                          self_join, p1.g.n_qtiles, lo.slice_rows,
-                                          lo.slice_qtiles, order_ws, stream, launches, &oo)) !=
-                cudaSuccess)
+            if (!self_join) {  // queries that are not base rows get their cells like the base did
+                if ((e = launch_order_clear_queries(ob, stream)) != cudaSuccess) return e;
+                if ((e = assign_cells(q_slice, rows, ob.cell_q, ob.hist_q)) != cudaSuccess) return e;
+            }
+            if ((e = launch_order_sort_queries(ob, s_begin, rows, self_join, p1.g.n_qtiles, stream,
+                                               launches, &oo)) != cudaSuccess)
                 return e;
         }
         // query operand of the slice
-        if (used_i8) {
-            prep_rows_i8_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(
-                q_slice, rows, d, lo.d32, static_cast<uint8_t *>(xq), self_join ? nullptr : qn_slice,
-                nullptr, 0, oo.q_perm, s_begin, sc);
-            ++*launches;
+        if (used_i8 || lo.order || !self_join) {
+            prep_rows(used_i8, q_slice, rows, xq, self_join ? nullptr : qn_slice, nullptr, false,
+                      oo.q_perm, s_begin);
             p1.a_op = xq;
             p1.a_rows = (uint64_t)rows;
             p1.q_op_begin = 0;
-        } else if (self_join && !lo.order) {
-            p1.a_op = xh_b;  // query q is operand row q of the base
+        } else {
+            p1.a_op = xh_b;  // FP16 self-join in natural order: query q is operand row q
             p1.a_rows = (uint64_t)nb;
             p1.q_op_begin = s_begin;
-        } else {
-            prep_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(
-                q_slice, rows, d, lo.d16, static_cast<__half *>(xq),
-                self_join ? nullptr : qn_slice, nullptr, 0, oo.q_perm, s_begin, sc);
-            ++*launches;
-            p1.a_op = xq;
-            p1.a_rows = (uint64_t)rows;
-            p1.q_op_begin = 0;
         }
         p1.L_exact = lo.L_exact;
         p1.L_inexact = lo.L;
         p1.gcap = lo.gcap;
         p1.nmma = lo.nmma;
+        p1.kcap = kcap;
+        p1.self_join = self_join;
         p1.streaming = lo.streaming;
+        p1.b_op = xh_b;
+        p1.b_fold = fold_b;
+        p1.nb_rows = nb;
+        p1.n_btiles = lo.n_btiles;
         p1.i8 = used_i8;
         p1.op_cols = used_i8 ? lo.d32 / 2 : lo.d16;
         p1.queries = q_slice;
@@ -1207,6 +1301,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         p1.fb_rows = fb_rows;
         p1.fb_count = &sc->fb_count;
         p1.ev3 = times ? &evs[2 + 3 * (size_t)si] : nullptr;
+        p1.pick_cell = p1.pick_hist = nullptr;
         if ((e = run_pass(p1)) != cudaSuccess) return e;
     }
 
@@ -1239,7 +1334,10 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                 if ((e = cudaMemsetAsync(&sc->maxabs_bits, 0, 3 * sizeof(uint32_t), stream)) !=
                     cudaSuccess)
                     return e;
-                prep_base_fp16();
+                prep_scale_fp16();
+                fold_const_kernel<<<(TC_ROWS * FOLD_COLS + 255) / 256, 256, 0, stream>>>(fold_a);
+                ++*launches;
+                prep_base(false);
             }
             float *q2 = reinterpret_cast<float *>(w + lo.p2_q);
             __half *xh2 = reinterpret_cast<__half *>(w + lo.p2_xh);
@@ -1263,7 +1361,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                 *launches += 2;
                 p2.q_self = nullptr;
                 if (lo.order && self_join) {
-                    if ((e = launch_order_self_of(ids, n2, oo.base_inv, self2, stream, launches)) !=
+                    if ((e = launch_order_self_of(ids, n2, ob.base_inv, self2, stream, launches)) !=
                         cudaSuccess)
                         return e;
                     p2.q_self = self2;
@@ -1274,7 +1372,14 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                 p2.L_exact = p2.L_inexact = L2;
                 p2.gcap = P2_GCAP;
                 p2.nmma = 1;
+                p2.kcap = kcap;
+                p2.self_join = self_join;
                 p2.streaming = stream2;
+                p2.b_op = xh_b;
+                p2.b_fold = fold_b;
+                p2.nb_rows = nb;
+                p2.n_btiles = lo.n_btiles;
+                p2.pick_cell = p2.pick_hist = nullptr;
                 p2.a_op = xh2;
                 p2.a_rows = (uint64_t)n2;
                 p2.q_op_begin = 0;

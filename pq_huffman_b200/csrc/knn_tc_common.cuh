@@ -80,6 +80,7 @@ struct TcArgs {
     int q_tail0, ns_tail, tiles_per_split_tail;
     int kcap;        // neighbours needed per row (k, or k-1 for a self-join)
     int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
+    int spin;        // accumulator hand-offs are polled instead of suspending the waiting threads
     int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
     const PrepScalars *sc;
     key64_t *cand;
@@ -343,21 +344,22 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
 
 // Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
 // it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
+// The 32 x 128 slice is copied to registers with two 64-column tcgen05.ld in flight together.
 //
-// Hot path (kept small and contiguous -- it must live in the instruction cache): copy the
-// 32 x 128 slice to registers with two 64-column tcgen05.ld in flight together, reduce it to
-// 16 group maxima (groups of 8 columns) with 3-input max -- level by level, so that sixteen
-// independent operations are in flight at any time -- compare with the row's threshold tau and
-// OR the 16-bit result over the warp.  No bit set (the common case): done.
-// Slow path, two flavours:
-//   EARLY  the accumulator stage is released as soon as the copy has landed (the tile then
-//          lives in registers and the tensor cores never wait for the filtering); flagged groups
-//          (warp-uniform test) are appended straight from the registers;
-//   !EARLY flagged groups are re-read from TMEM by address in one small loop (no unrolled
-//          copies) and the stage is released after that -- before the scan when at most two
-//          groups are flagged.
-// Either way scores above tau go to the row's candidate list with predicated stores (no
-// divergent branches), and a list that reached its hard capacity is shrunk (rare).
+// EARLY: the accumulator stage is released as soon as the copy has landed -- the tile then lives
+//   in registers and the tensor cores never wait for the filtering, only for the copy.  (With a
+//   short K the accumulator hand-offs dominate: one 256 x 128 kind::i8 tile is 640 cycles of MMA
+//   against ~900 cycles of commit / wake-up / release latencies, and the two stages TMEM has room
+//   for cannot hide a filter on top of that.)  Hot path: four independent running maxima with
+//   3-input max give the row maximum (the 128 values have to stay live, so there is no register
+//   room for per-group maxima); one compare with the row's threshold tau and one vote.  Nothing
+//   above tau in any row of the warp (the common case): done.  Slow path: every group of 8
+//   columns is tested (warp-uniform) and the scores above tau are appended, straight from the
+//   registers, with predicated stores.
+// !EARLY: 16 group maxima level by level, vote, then the flagged groups are re-read from TMEM by
+//   address in one small loop and the stage is released after that (before the scan when at
+//   most two groups are flagged).
+// Either way a list that reached its hard capacity is shrunk (rare).
 template <int GCAP, bool I8, bool EARLY, class Release>
 __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
                                             int self, int L, int lane, int debug_mode,
@@ -370,47 +372,78 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
     ptx::tmem_ld_32x32b_x64(tbase, ra);
     ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
     ptx::tmem_wait_ld();
-    if (EARLY) release();
 #define PQH_V(q, j) S::from_bits(((q) < 8) ? ra[(q) * 8 + (j)] : rb[((q) - 8) * 8 + (j)])
-    T gm[NG];
-#pragma unroll
-    for (int q = 0; q < NG; ++q) gm[q] = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
-#pragma unroll
-    for (int q = 0; q < NG; ++q) gm[q] = S::max3(gm[q], PQH_V(q, 3), PQH_V(q, 4));
-#pragma unroll
-    for (int q = 0; q < NG; ++q) gm[q] = S::max3(gm[q], PQH_V(q, 5), PQH_V(q, 6));
-#pragma unroll
-    for (int q = 0; q < NG; ++q) gm[q] = S::max2(gm[q], PQH_V(q, 7));
-    const T r0 = S::max3(gm[0], gm[1], gm[2]), r1 = S::max3(gm[3], gm[4], gm[5]);
-    const T r2 = S::max3(gm[6], gm[7], gm[8]), r3 = S::max3(gm[9], gm[10], gm[11]);
-    const T r4 = S::max3(gm[12], gm[13], gm[14]);
-    const T rm = S::max3(S::max3(r0, r1, r2), S::max3(r3, r4, gm[15]), S::lowest());
-    // common case: no row of the warp has anything above its threshold -> one vote, done
-    if (!__any_sync(0xffffffffu, rm > tau) || debug_mode == 2) {
-        if (!EARLY) release();
-        return;
-    }
-    unsigned gmask = 0;
-#pragma unroll
-    for (int q = 0; q < NG; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
-    unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
-    ++slow_tiles;
-    // ragged last tile / the row's own column: only "special" tiles carry a real limit
-    const int id_lim = special ? ib_hi : 0x7fffffff;
     if constexpr (EARLY) {
+        release();
+        // "special" tiles (ragged last tile, the row's own column): take the forbidden columns
+        // out here, once, so that the scan below tests scores only
+        if (__any_sync(0xffffffffu, special)) {
+            const int id_lim = special ? ib_hi : 0x7fffffff;
+            uint32_t low;
+            if constexpr (I8) low = 0x80000000u;
+            else low = 0xff800000u;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                if (col_base + c >= id_lim || col_base + c == self) ra[c] = low;
+                if (col_base + 64 + c >= id_lim || col_base + 64 + c == self) rb[c] = low;
+            }
+        }
+        T m0 = S::max3(PQH_V(0, 0), PQH_V(0, 1), PQH_V(0, 2));
+        T m1 = S::max3(PQH_V(4, 0), PQH_V(4, 1), PQH_V(4, 2));
+        T m2 = S::max3(PQH_V(8, 0), PQH_V(8, 1), PQH_V(8, 2));
+        T m3 = S::max3(PQH_V(12, 0), PQH_V(12, 1), PQH_V(12, 2));
+#pragma unroll
+        for (int c = 3; c < 31; c += 2) {  // columns 3..30 of each 32-column quarter, pairwise
+            m0 = S::max3(m0, PQH_V(c >> 3, c & 7), PQH_V((c + 1) >> 3, (c + 1) & 7));
+            m1 = S::max3(m1, PQH_V(4 + (c >> 3), c & 7), PQH_V(4 + ((c + 1) >> 3), (c + 1) & 7));
+            m2 = S::max3(m2, PQH_V(8 + (c >> 3), c & 7), PQH_V(8 + ((c + 1) >> 3), (c + 1) & 7));
+            m3 = S::max3(m3, PQH_V(12 + (c >> 3), c & 7), PQH_V(12 + ((c + 1) >> 3), (c + 1) & 7));
+        }
+        m0 = S::max3(m0, PQH_V(3, 7), m1);
+        m2 = S::max3(m2, PQH_V(7, 7), m3);
+        const T rm = S::max3(S::max3(m0, m2, PQH_V(11, 7)), PQH_V(15, 7), S::lowest());
+        if (!__any_sync(0xffffffffu, rm > tau) || debug_mode == 2) return;
+        ++slow_tiles;
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-            if (groups & (1u << q)) {  // warp-uniform
+            T m = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
+            m = S::max3(m, PQH_V(q, 3), PQH_V(q, 4));
+            m = S::max3(m, PQH_V(q, 5), PQH_V(q, 6));
+            m = S::max2(m, PQH_V(q, 7));
+            if (__any_sync(0xffffffffu, m > tau)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int id = col_base + q * 8 + j;
                     const uint32_t bits = (q < 8) ? ra[q * 8 + j] : rb[(q - 8) * 8 + j];
-                    const bool p = (S::from_bits(bits) > tau) & (id < id_lim) & (id != self);
-                    append_if<I8>(p, list, cnt, bits, id);
+                    append_if<I8>(S::from_bits(bits) > tau, list, cnt, bits, col_base + q * 8 + j);
                 }
             }
         }
     } else {
+        T gm[NG];
+#pragma unroll
+        for (int q = 0; q < NG; ++q) gm[q] = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
+#pragma unroll
+        for (int q = 0; q < NG; ++q) gm[q] = S::max3(gm[q], PQH_V(q, 3), PQH_V(q, 4));
+#pragma unroll
+        for (int q = 0; q < NG; ++q) gm[q] = S::max3(gm[q], PQH_V(q, 5), PQH_V(q, 6));
+#pragma unroll
+        for (int q = 0; q < NG; ++q) gm[q] = S::max2(gm[q], PQH_V(q, 7));
+        const T r0 = S::max3(gm[0], gm[1], gm[2]), r1 = S::max3(gm[3], gm[4], gm[5]);
+        const T r2 = S::max3(gm[6], gm[7], gm[8]), r3 = S::max3(gm[9], gm[10], gm[11]);
+        const T r4 = S::max3(gm[12], gm[13], gm[14]);
+        const T rm = S::max3(S::max3(r0, r1, r2), S::max3(r3, r4, gm[15]), S::lowest());
+        // common case: no row of the warp has anything above its threshold -> one vote, done
+        if (!__any_sync(0xffffffffu, rm > tau) || debug_mode == 2) {
+            release();
+            return;
+        }
+        unsigned gmask = 0;
+#pragma unroll
+        for (int q = 0; q < NG; ++q) gmask |= (gm[q] > tau) ? (1u << q) : 0u;
+        unsigned groups = __reduce_or_sync(0xffffffffu, gmask);
+        ++slow_tiles;
+        // ragged last tile / the row's own column: only "special" tiles carry a real limit
+        const int id_lim = special ? ib_hi : 0x7fffffff;
         auto scan8 = [&](const uint32_t(&v8)[8], int q) {
             const int col0 = col_base + q * 8;
 #pragma unroll
@@ -460,13 +493,15 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
 // the body runs full-mask collectives.
 template <int GCAP, bool I8>
 __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
-                                                           int lane, typename Score<I8>::T &tau,
-                                                           int &cnt, key64_t *list) {
+                                                           int lane, bool spin,
+                                                           typename Score<I8>::T &tau, int &cnt,
+                                                           key64_t *list) {
     const int soft = (L + L / 2 < GCAP - TC_BN) ? L + L / 2 : GCAP - TC_BN;
     while (!__all_sync(0xffffffffu, ptx::mbar_test_wait(bar, parity))) {
         const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
         if (need == 0) {
-            ptx::mbar_wait(bar, parity);
+            if (spin) ptx::mbar_spin(bar, parity);
+            else ptx::mbar_wait(bar, parity);
             return;
         }
         shrink_flagged<GCAP, I8, true>(need & (0u - need), L, lane, tau, cnt, list);
@@ -523,7 +558,8 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
             const uint32_t s = gstep + (uint32_t)i;
             const int as = (int)(s & 1u);
             const uint32_t acc_ph = (s >> 1) & 1u;
-            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
+            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, args.spin != 0,
+                                                 tau, cnt, list);
             ptx::tc_fence_after_sync();
             if (i == 0) {
                 ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);

@@ -161,7 +161,8 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 const ItemInfo it = decode_item(args, item);
                 const int t_lo = it.t_lo, t_hi = it.t_hi;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {
-                    ptx::mbar_wait(&tail.eb.acc_empty[as], acc_ph ^ 1);
+                    if (args.spin) ptx::mbar_spin(&tail.eb.acc_empty[as], acc_ph ^ 1);
+                    else ptx::mbar_wait(&tail.eb.acc_empty[as], acc_ph ^ 1);
                     ptx::tc_fence_after_sync();
                     for (int i = 0; i < kb.total; ++i) {
                         int bytes, k_off, fold;

@@ -40,14 +40,23 @@ def _check_properties(a, dist, n):
 
 
 def _check_rows_against_oracle(x, a, dist, k, rows):
+    """Self-join rows `rows` of the result against the oracle.  The sampled rows go to the oracle
+    as one batch of distinct queries (it threads over queries); its answer for query x[r] holds r
+    itself at distance 0, which the self-join convention moves to column 0 and drops from the
+    ranking (compute_nn_fast.c:498), so it is taken out of the oracle's k+1 neighbours here."""
     orc = oracle_ffi.Oracle()
-    for r in rows:
-        ea, ed = orc.knn_rows(x, None, k, int(r), int(r) + 1)
-        assert np.array_equal(a[r], ea[0]), f"row {r}: ids differ"
-        assert np.array_equal(dist[r].view(np.uint32), ed[0].view(np.uint32)), f"row {r}: distances"
+    rows = np.asarray(rows, dtype=np.int64)
+    ea, ed = orc.knn(x, np.ascontiguousarray(x[rows]), k + 1)
+    for i, r in enumerate(rows):
+        keep = ea[i] != r
+        assert keep.sum() >= k - 1, f"row {r}: own vector missing from the oracle's neighbours"
+        exp_a = np.concatenate([[r], ea[i][keep][:k - 1]]).astype(np.int32)
+        exp_d = np.concatenate([[np.float32(0.0)], ed[i][keep][:k - 1]]).astype(np.float32)
+        assert np.array_equal(a[r], exp_a), f"row {r}: ids differ"
+        assert np.array_equal(dist[r].view(np.uint32), exp_d.view(np.uint32)), f"row {r}: distances"
 
 
-def _sampled_and_uncertified(n, n_sample, seed, cap=1500):
+def _sampled_and_uncertified(n, n_sample, seed, cap=2000):
     """n_sample random rows plus the rows the first pass left open (all of them up to `cap`)."""
     rng = np.random.default_rng(seed)
     rows = set(int(r) for r in rng.choice(n, n_sample, replace=False))

@@ -190,9 +190,12 @@ def test_tensor_path_boundaries(oracle, n, d, k):
 KNOBS = [
     dict(PQH_TC_MMA=2),
     dict(PQH_TC_ORDER=0),
-    dict(PQH_TC_ORDER=0, PQH_TC_MMA=2),
+    dict(PQH_TC_ORDER=0, PQH_TC_MMA=2, PQH_TC_SPIN=1),
+    dict(PQH_TC_EARLY=1),
+    dict(PQH_TC_EARLY=1, PQH_TC_MMA=2, PQH_TC_SPIN=1),
+    dict(PQH_TC_EARLY=1, PQH_TC_ORDER=0, PQH_TC_I8=0),
     dict(PQH_TC_STREAM=1),
-    dict(PQH_TC_STREAM=1, PQH_TC_ORDER=0),
+    dict(PQH_TC_STREAM=1, PQH_TC_ORDER=0, PQH_TC_SPIN=1),
     dict(PQH_TC_I8=0, PQH_TC_MMA=2),
     dict(PQH_TC_SLICE_MB=64),
 ]
@@ -204,9 +207,9 @@ _KNOB_CASES = {}
 def _knob_cases(oracle):
     """Inputs and oracle answers shared by every configuration (computed once)."""
     if not _KNOB_CASES:
-        x = synth.with_duplicates_and_ties(synth.sift_like(20000, 128, seed=77), n_dups=6, n_ties=6)
-        g = synth.gist_like(9000, 96, seed=78)
-        b = synth.deep_like(9000, 96, seed=79)
+        x = synth.with_duplicates_and_ties(synth.sift_like(40000, 128, seed=77), n_dups=6, n_ties=6)
+        g = synth.gist_like(33000, 96, seed=78)
+        b = synth.deep_like(34000, 96, seed=79)
         v = synth.deep_like(700, 96, seed=80)
         _KNOB_CASES.update(x=x, g=g, b=b, v=v, ex=oracle.knn(x, None, 17), eg=oracle.knn(g, None, 9),
                            ebv=oracle.knn(b, v, 33))
@@ -215,9 +218,10 @@ def _knob_cases(oracle):
 
 @pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a[7:]}={b}" for a, b in k.items()))
 def test_kernel_configurations_stay_exact(tc_env, oracle, knobs):
-    """Every selectable configuration of the tensor-core path -- one or two MMA issuers, locality
-    order on or off, the streaming kernel forced on a small d, small row slices -- must produce
-    the oracle's answer: the knobs only decide how fast."""
+    """Every selectable configuration of the tensor-core path -- one or two MMA issuers, stage
+    release before or after the filtering, polled or suspended barrier waits, locality order on
+    or off, the streaming kernel forced on a small d, small row slices -- must produce the
+    oracle's answer: the knobs only decide how fast."""
     c = _knob_cases(oracle)
     tc_env(**knobs)
     got = knn.knn_full_thread(c["x"], None, 17)
@@ -225,8 +229,8 @@ def test_kernel_configurations_stay_exact(tc_env, oracle, knobs):
     assert_rows_equal(got, c["ex"])
     assert_rows_equal(knn.knn_full_thread(c["g"], None, 9), c["eg"])
     assert_rows_equal(knn.knn_full_thread(c["b"], c["v"], 33), c["ebv"])
-    a, dd = knn.search_rows(c["x"], None, 17, 5000, 12345)
-    assert_rows_equal((a, dd), (c["ex"][0][5000:12345], c["ex"][1][5000:12345]))
+    a, dd = knn.search_rows(c["x"], None, 17, 5000, 32345)
+    assert_rows_equal((a, dd), (c["ex"][0][5000:32345], c["ex"][1][5000:32345]))
 
 
 def test_row_slices_bound_the_scratch(tc_env, oracle):
@@ -242,6 +246,17 @@ def test_row_slices_bound_the_scratch(tc_env, oracle):
     tc_env(PQH_TC_SLICE_MB=None)
     # Deep10M-shaped: operands 1.9 GB + lists of one slice, not 41 GB of lists
     assert knn.workspace_bytes(10_000_000, 10_000_000, 96, 33) <= 8 * 2**30
+
+
+def test_list_capacity_with_long_candidate_lists(oracle):
+    """k = 33 distinct queries keep L = 96 candidates per row: a shrink leaves up to 144 entries and
+    a tile may add 128 more, so the lists need the 512-entry capacity (a 256-entry list overflowed
+    here, intermittently, in the first tiles of a sweep)."""
+    b = synth.deep_like(40000, 96, seed=91)
+    v = synth.deep_like(1500, 96, seed=92)
+    exp = oracle.knn(b, v, 33)
+    for _ in range(3):
+        assert_rows_equal(knn.knn_full_thread(b, v, 33), exp)
 
 
 def test_mass_duplicates_through_tensor_path(oracle):

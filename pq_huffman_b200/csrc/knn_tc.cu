@@ -52,9 +52,9 @@ namespace {
 struct TcEnv {
     int i8 = 1;        // PQH_TC_I8: integer tensor-core path for uint8-valued data
     int order = 1;     // PQH_TC_ORDER: locality order of the sweep (knn_order.cu)
-    int nmma = 1;      // PQH_TC_MMA: MMA-issuing threads per CTA, 1 or 2
-    int early = 0;     // PQH_TC_EARLY: release the accumulator stage before filtering
-    int spin = 0;      // PQH_TC_SPIN: poll the accumulator barriers instead of suspending
+    int nmma = 2;      // PQH_TC_MMA: MMA-issuing threads per CTA, 1 or 2
+    int early = 1;     // PQH_TC_EARLY: release the accumulator stage before filtering (0: after)
+    int own_tiles = 8; // PQH_TC_OWN: tiles of the own-cell window a sweep starts with
     int l_exact = 0, l_inexact = 0;  // PQH_TC_LEXACT / PQH_TC_LINEXACT: candidates kept per row
     int gcap = 0;      // PQH_TC_GCAP: list capacity, 256 or 512
     int nsplit = 0;    // PQH_TC_NSPLIT: base splits
@@ -232,13 +232,7 @@ struct TcSmemTail {
 };
 
 // both barriers of an MMA step probed together: their latencies overlap instead of adding up
-__device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *b1, uint32_t p1,
-                                           bool spin) {
-    if (spin) {
-        ptx::mbar_spin(b0, p0);
-        ptx::mbar_spin(b1, p1);
-        return;
-    }
+__device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *b1, uint32_t p1) {
     const bool ok0 = ptx::mbar_try_wait(b0, p0);
     const bool ok1 = ptx::mbar_try_wait(b1, p1);
     if (!ok0) ptx::mbar_wait_slow(b0, p0);
@@ -303,9 +297,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 const ItemInfo it = decode_item(args, item);
                 const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
                 ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
-                const int t0 = item_start_tile(args, qt, t_lo, t_hi, my_next);
-                my_next = t0;  // a full sweep ends where it started
-                tail.eb.item_t0[it_par] = t0;
+                const ItemOrder ord = item_order(args, qt, t_lo, t_hi, my_next);
+                const int wlen = own_window_len(args, t_lo, t_hi);
+                tail.eb.item_w0[it_par] = ord.w0;
+                tail.eb.item_uc[it_par] = ord.uc;
                 ptx::mbar_arrive(&tail.eb.t0_ready);
                 ptx::mbar_arrive_expect_tx(&tail.a_full, plan.a_bytes);
                 for (int s = 0; s < plan.nseg; ++s) {
@@ -319,8 +314,9 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 a_ph ^= 1;
                 it_par ^= 1;
                 for (int i = 0; i < t_hi - t_lo; ++i) {
-                    const int t = item_tile(i, t0, t_lo, t_hi);
-                    if ((i & 7) == 0) publish_cursor(args, t);
+                    const int t = item_tile(i, ord, wlen, t_lo, t_hi);
+                    if (i == wlen) my_next = t;  // the cyclic part ends where it started
+                    if (i >= wlen && (i & 7) == 0) publish_cursor(args, t);
                     ptx::mbar_wait(&tail.b_empty[stage], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&tail.b_full[stage], plan.b_bytes);
                     uint8_t *dst = smB + stage * plan.b_bytes;
@@ -361,8 +357,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     const int stage = (int)(s % TC_NSTAGE), as = (int)(s & 1u);
                     const uint32_t ph = (s / TC_NSTAGE) & 1u, acc_ph = (s >> 1) & 1u;
                     const long long w0 = prof ? clock64() : 0;
-                    mbar_wait2(&tail.b_full[stage], ph, &tail.eb.acc_empty[as], acc_ph ^ 1,
-                               args.spin != 0);
+                    mbar_wait2(&tail.b_full[stage], ph, &tail.eb.acc_empty[as], acc_ph ^ 1);
                     if (prof) t_wait += clock64() - w0;
                     ptx::tc_fence_after_sync();
                     const uint32_t b_base = ptx::smem_u32(smB + stage * plan.b_bytes);
@@ -882,9 +877,10 @@ void tc_reload_env() {
     TcEnv e;
     e.i8 = env_int("PQH_TC_I8", 1) != 0;
     e.order = env_int("PQH_TC_ORDER", 1) != 0;
-    e.nmma = env_int("PQH_TC_MMA", 1) == 2 ? 2 : 1;
-    e.early = env_int("PQH_TC_EARLY", 0) != 0;
-    e.spin = env_int("PQH_TC_SPIN", 0) != 0;
+    e.nmma = env_int("PQH_TC_MMA", 2) == 1 ? 1 : 2;
+    e.early = env_int("PQH_TC_EARLY", 1) != 0;
+    e.own_tiles = env_int("PQH_TC_OWN", 8);
+    if (e.own_tiles < 1) e.own_tiles = 1;
     e.l_exact = env_int("PQH_TC_LEXACT", 0);
     e.l_inexact = env_int("PQH_TC_LINEXACT", 0);
     e.gcap = env_int("PQH_TC_GCAP", 0);
@@ -1087,7 +1083,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         args.tiles_per_split = p.g.tiles_per_split;
         args.n_btiles = p.n_btiles;
         args.debug_mode = p.pick_cell ? 0 : debug_mode;
-        args.spin = ev.spin;
+        args.own_tiles = ev.own_tiles;
         args.kcap = p.kcap;
         args.L_exact = p.L_exact;
         args.L_inexact = p.L_inexact;

@@ -80,7 +80,7 @@ struct TcArgs {
     int q_tail0, ns_tail, tiles_per_split_tail;
     int kcap;        // neighbours needed per row (k, or k-1 for a self-join)
     int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
-    int spin;        // accumulator hand-offs are polled instead of suspending the waiting threads
+    int own_tiles;   // locality order: tiles of the own-cell window a sweep starts with
     int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
     const PrepScalars *sc;
     key64_t *cand;
@@ -129,31 +129,57 @@ __host__ __device__ __forceinline__ size_t list_slot(int r, int sp, int tail_row
 }
 
 // Base-tile order of one work item.  Every CTA sweeps ALL tiles of its range, so the order is
-// free.
-//  * Locality order (qt_start given): the sweep starts at the cell the query tile's own rows
-//    belong to, so a row meets its near neighbours in the first few tiles and its threshold is
-//    tight for the rest of the sweep.  CTAs work on neighbouring query tiles at any moment, so
-//    they still stream one window of the base together.
-//  * Natural order: CTA 0 never restarts -- it keeps cycling through the tiles and publishes
-//    its position -- and every other CTA starts a new item at CTA 0's current tile and wraps
-//    around.  All CTAs then stream the same window of the base operand at any moment, and a
-//    tile is fetched from HBM once per sweep of the pack instead of once per CTA.  (Single
-//    writer: a cursor written by every CTA never converges.)
-__device__ __forceinline__ int item_start_tile(const TcArgs &a, int qt, int t_lo, int t_hi,
-                                               int my_next) {
+// free, and two things are wanted from it:
+//  * Locality order (qt_start given): the sweep STARTS with a window of a few tiles at
+//    the cell the query tile's own rows belong to, so a row meets its near neighbours first and
+//    its threshold is tight for the rest of the sweep.
+//  * The rest of the range is swept cyclically from wherever CTA 0 currently is: CTA 0 never
+//    restarts -- it keeps cycling through the tiles and publishes its position -- and every
+//    other CTA joins the sweep there and wraps around.  All CTAs then stream the same window of
+//    the base operand at any moment, and a tile is fetched from HBM once per sweep of the pack
+//    instead of once per CTA (measured without it, every CTA starting at its own cell: 146 GB
+//    of DRAM reads per SIFT1M launch instead of 5).  (Single writer: a cursor written by every
+//    CTA never converges.)
+// An order is (w0, uc): first tile of the own window and the start of the cyclic part, as an
+// index into the range with the window cut out.
+struct ItemOrder {
+    int w0, uc;
+};
+__device__ __forceinline__ int own_window_len(const TcArgs &a, int t_lo, int t_hi) {
+    const int n = t_hi - t_lo;
+    return a.qt_start ? (n < a.own_tiles ? n : a.own_tiles) : 0;
+}
+// producer side: my_next = where CTA 0's own cyclic sweep continues
+__device__ __forceinline__ ItemOrder item_order(const TcArgs &a, int qt, int t_lo, int t_hi,
+                                                int my_next) {
+    const int n = t_hi - t_lo, wlen = own_window_len(a, t_lo, t_hi);
+    ItemOrder o;
+    o.w0 = t_lo;
+    if (wlen) {
+        int s = a.qt_start[qt];
+        if (s < t_lo || s >= t_hi) s = t_lo;  // the cell lies in another base split
+        o.w0 = s < t_hi - wlen ? s : t_hi - wlen;
+    }
     int c = my_next;
-    if (a.qt_start)
-        c = a.qt_start[qt];
-    else if (blockIdx.x != 0)
+    if (blockIdx.x != 0)
         c = (int)*reinterpret_cast<const volatile uint32_t *>(&a.sc->tile_cursor);
-    return (c >= t_lo && c < t_hi) ? c : t_lo;
+    if (c < t_lo || c >= t_hi) c = t_lo;
+    o.uc = c < o.w0 ? c - t_lo : (c >= o.w0 + wlen ? c - t_lo - wlen : o.w0 - t_lo);
+    if (o.uc >= n - wlen) o.uc = 0;
+    return o;
 }
-__device__ __forceinline__ int item_tile(int i, int t0, int t_lo, int t_hi) {
-    int t = t0 + i;
-    return t >= t_hi ? t - (t_hi - t_lo) : t;
+// tile of step i of the item
+__device__ __forceinline__ int item_tile(int i, ItemOrder o, int wlen, int t_lo, int t_hi) {
+    if (i < wlen) return o.w0 + i;
+    const int m = t_hi - t_lo - wlen;
+    int u = o.uc + (i - wlen);
+    if (u >= m) u -= m;
+    const int t = t_lo + u;
+    return t >= o.w0 ? t + wlen : t;
 }
+// CTA 0 publishes its position in the cyclic part
 __device__ __forceinline__ void publish_cursor(const TcArgs &a, int t) {
-    if (blockIdx.x == 0 && !a.qt_start)
+    if (blockIdx.x == 0)
         *reinterpret_cast<volatile uint32_t *>(&const_cast<PrepScalars *>(a.sc)->tile_cursor) =
             (uint32_t)t;
 }
@@ -486,34 +512,32 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
                                     cnt, list);
 }
 
-// While the tensor cores have not finished the next accumulator tile, use the idle time to
-// shrink lists that have grown past 1.5 L: the threshold then stays fresh without a shrink ever
-// standing between a finished accumulator stage and its release (mandatory shrinks at the hard
-// capacity remain in filter_tile, but become rare).  The loop condition is made warp-uniform:
-// the body runs full-mask collectives.
+// Wait for the next accumulator tile.  If some list of the warp has grown past 1.5 L and the
+// tensor cores are not done yet, the idle time goes into shrinking it: the threshold then stays
+// fresh without a shrink ever standing between a finished accumulator stage and its release
+// (mandatory shrinks at the hard capacity remain in filter_tile, but become rare).  The common
+// case -- nothing to shrink -- goes straight to the suspending wait, which resumes ~60 cycles
+// after the barrier flips (a non-blocking probe costs ~150 cycles even when the phase is
+// already complete).  Loop conditions are warp-uniform: the body runs full-mask collectives.
 template <int GCAP, bool I8>
 __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
-                                                           int lane, bool spin,
-                                                           typename Score<I8>::T &tau, int &cnt,
-                                                           key64_t *list) {
+                                                           int lane, typename Score<I8>::T &tau,
+                                                           int &cnt, key64_t *list) {
     const int soft = (L + L / 2 < GCAP - TC_BN) ? L + L / 2 : GCAP - TC_BN;
-    while (!__all_sync(0xffffffffu, ptx::mbar_test_wait(bar, parity))) {
-        const unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
-        if (need == 0) {
-            if (spin) ptx::mbar_spin(bar, parity);
-            else ptx::mbar_wait(bar, parity);
-            return;
-        }
+    unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
+    while (need != 0 && !__all_sync(0xffffffffu, ptx::mbar_test_wait(bar, parity))) {
         shrink_flagged<GCAP, I8, true>(need & (0u - need), L, lane, tau, cnt, list);
+        need = __ballot_sync(0xffffffffu, cnt > soft);
     }
+    ptx::mbar_wait(bar, parity);
 }
 
 // Barriers and hand-over words the filter warps use, in the shared-memory tail of both kernels.
 struct EpiBars {
     uint64_t acc_full[2], acc_empty[2];
-    uint64_t t0_ready;  // producer -> epilogue: item_t0 of the next item is written
+    uint64_t t0_ready;  // producer -> epilogue: the order of the next item is written
     uint32_t tmem_base;
-    int item_t0[2];     // first base tile of the current / next work item (set by the producer)
+    int item_w0[2], item_uc[2];  // tile order of the current / next work item (ItemOrder)
 };
 
 // The filter warps of one CTA: filter warp e (0 .. 7) owns TMEM lane quadrant `quad` (= its
@@ -553,19 +577,20 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
         const int ib_hi = (int)b_hi;
 
         const int nst = t_hi - t_lo;
-        int t0 = 0;
+        const int wlen = own_window_len(args, t_lo, t_hi);
+        ItemOrder ord = {t_lo, 0};
         for (int i = 0; i < nst; ++i) {
             const uint32_t s = gstep + (uint32_t)i;
             const int as = (int)(s & 1u);
             const uint32_t acc_ph = (s >> 1) & 1u;
-            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, args.spin != 0,
-                                                 tau, cnt, list);
+            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
             ptx::tc_fence_after_sync();
             if (i == 0) {
                 ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
-                t0 = *reinterpret_cast<volatile int *>(&eb->item_t0[it_par]);
+                ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
+                ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
             }
-            const int t = item_tile(i, t0, t_lo, t_hi);
+            const int t = item_tile(i, ord, wlen, t_lo, t_hi);
             const uint32_t tbase = tmem_row + (uint32_t)(as * 256);
             // id checks are only needed in the tile holding this row's own column and in
             // the (possibly ragged) last tile

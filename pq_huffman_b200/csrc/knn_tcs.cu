@@ -120,14 +120,16 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 const int arow = args.q_op_begin + qt * TC_ROWS;
                 // the slot of item i is reused by item i+2; the producer is at most one ring
                 // (a fraction of a tile) ahead of the MMA, the epilogue at most two tiles behind
-                const int t0 = item_start_tile(args, qt, t_lo, t_hi, my_next);
-                my_next = t0;
-                tail.eb.item_t0[it_par] = t0;
+                const ItemOrder ord = item_order(args, qt, t_lo, t_hi, my_next);
+                const int wlen = own_window_len(args, t_lo, t_hi);
+                tail.eb.item_w0[it_par] = ord.w0;
+                tail.eb.item_uc[it_par] = ord.uc;
                 ptx::mbar_arrive(&tail.eb.t0_ready);
                 it_par ^= 1;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {
-                    const int t = item_tile(ti, t0, t_lo, t_hi);
-                    publish_cursor(args, t);
+                    const int t = item_tile(ti, ord, wlen, t_lo, t_hi);
+                    if (ti == wlen) my_next = t;
+                    if (ti >= wlen) publish_cursor(args, t);
                     for (int i = 0; i < kb.total; ++i) {
                         int bytes, k_off, fold;
                         kb.get(i, bytes, k_off, fold);
@@ -161,8 +163,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 const ItemInfo it = decode_item(args, item);
                 const int t_lo = it.t_lo, t_hi = it.t_hi;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {
-                    if (args.spin) ptx::mbar_spin(&tail.eb.acc_empty[as], acc_ph ^ 1);
-                    else ptx::mbar_wait(&tail.eb.acc_empty[as], acc_ph ^ 1);
+                    ptx::mbar_wait(&tail.eb.acc_empty[as], acc_ph ^ 1);
                     ptx::tc_fence_after_sync();
                     for (int i = 0; i < kb.total; ++i) {
                         int bytes, k_off, fold;

@@ -85,19 +85,6 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
-// Polling wait: probes the barrier instead of suspending the thread, so the waiter reacts a
-// few cycles after the phase flips (a suspended thread takes ~100 cycles longer to resume; on
-// the accumulator hand-offs of a short-K GEMM that latency is on the critical path).  Same
-// watchdog as above.
-static __device__ __noinline__ void mbar_spin_timeout(uint64_t *bar, uint32_t parity) {
-    printf("libpqh_knn: mbarrier poll timed out (block %d thread %d bar %u parity %u)\n",
-           (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-    __trap();
-}
-__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_test_wait(bar, parity); ++spins)
-        if (spins > (1u << 30)) mbar_spin_timeout(bar, parity);
-}
 
 // ---- TMA ----------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {

@@ -244,7 +244,9 @@ __device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *
 // accumulator stage m), so the barrier round trips of one overlap the MMAs of the other.
 // Steps are numbered over the life of the CTA: B ring stage = step % 4, accumulator stage =
 // step & 1.
-template <int GCAP, bool I8, int NMMA, bool EARLY>
+// MODE: 0 = filter, stage released after the filtering; 1 = filter, stage released early;
+// 2 = arg-max (cell assignment of the locality order).
+template <int GCAP, bool I8, int NMMA, int MODE>
 __global__ void __launch_bounds__(tc_threads(NMMA), 1)
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -399,7 +401,10 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         }
     } else {
         // ===================== epilogue: threshold filter =====================
-        epilogue_warps<GCAP, I8, EARLY>(args, warp - EPI0, warp & 3, lane, &tail.eb);
+        if constexpr (MODE == 2)
+            epilogue_warps_argmax<I8>(args, warp - EPI0, warp & 3, lane, &tail.eb);
+        else
+            epilogue_warps<GCAP, I8, MODE == 1>(args, warp - EPI0, warp & 3, lane, &tail.eb);
     }
 
     ptx::tc_fence_before_sync();
@@ -439,13 +444,23 @@ struct RerankArgs {
     uint32_t *fb_count;
 };
 
-template <int NMAX>
+// WIDE (large d, rows 16-byte aligned): a lane still owns one candidate and sums its d terms in
+// index order, but the candidate rows are FETCHED by the whole warp -- 256 contiguous bytes of
+// two rows per load instruction -- and handed to their lanes through a shared-memory tile.  With
+// one scattered 16-byte load per lane (the narrow path) a d = 960 re-rank is bound by the rate of
+// sector requests (32 different rows per instruction), not by bytes.
+constexpr int RR_DC = 64;        // floats of a row per tile chunk
+constexpr int RR_TSTR = RR_DC + 4;  // tile row stride: 16-byte aligned, conflict-free LDS.128
+
+template <int NMAX, bool WIDE>
 __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankArgs a) {
     extern __shared__ __align__(16) unsigned char rr_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     key64_t *keys = reinterpret_cast<key64_t *>(rr_smem) + (size_t)warp * NMAX;
     float *qrow = reinterpret_cast<float *>(rr_smem + (size_t)RR_WARPS * NMAX * sizeof(key64_t)) +
                   (size_t)warp * a.d;
+    float *tile = reinterpret_cast<float *>(rr_smem + (size_t)RR_WARPS * NMAX * sizeof(key64_t)) +
+                  (size_t)RR_WARPS * a.d + (size_t)warp * 32 * RR_TSTR;  // WIDE only
     const int r = blockIdx.x * RR_WARPS + warp;
     if (r >= a.n_rows) return;
     const int q = a.q_perm ? a.q_perm[r] : (a.row_ids ? a.row_ids[r] : a.q_begin + r);
@@ -517,27 +532,67 @@ __global__ void __launch_bounds__(RR_WARPS * 32) knn_rerank_kernel(const RerankA
 
     // exact distances: the scalar sequence of get_real_dist, one candidate per lane; keys are
     // rebuilt on (distance, base row) so that ties order by the caller's row numbers
-    for (int i = lane; i < n; i += 32) {
-        const uint32_t id = key_pos(keys[i]);
-        const float *brow = a.base + (size_t)id * a.d;
-        float acc = 0.0f;
-        if ((a.d & 3) == 0) {
-            const float4 *b4 = reinterpret_cast<const float4 *>(brow);
-            for (int j = 0; j < a.d / 4; ++j) {
-                const float4 bv = __ldg(b4 + j);
-                float t;
-                t = __fsub_rn(qrow[4 * j + 0], bv.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(qrow[4 * j + 1], bv.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(qrow[4 * j + 2], bv.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(qrow[4 * j + 3], bv.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+    if constexpr (WIDE) {
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int nbatch = n - b0 < 32 ? n - b0 : 32;
+            const uint32_t my_id = lane < nbatch ? key_pos(keys[b0 + lane]) : 0u;
+            float acc = 0.0f;
+            for (int j0 = 0; j0 < a.d; j0 += RR_DC) {
+                float4 stage[16];
+                const int off = j0 + (lane & 15) * 4;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = 2 * i + (lane >> 4);
+                    const uint32_t cid = __shfl_sync(0xffffffffu, my_id, c);
+                    stage[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < nbatch && off < a.d)
+                        stage[i] = __ldg(reinterpret_cast<const float4 *>(a.base + (size_t)cid * a.d + off));
+                }
+                __syncwarp();  // the previous chunk has been consumed
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    *reinterpret_cast<float4 *>(tile + (2 * i + (lane >> 4)) * RR_TSTR + (lane & 15) * 4) =
+                        stage[i];
+                __syncwarp();
+                if (lane < nbatch) {
+                    const float *tr = tile + lane * RR_TSTR;
+                    const int jn = a.d - j0 < RR_DC ? a.d - j0 : RR_DC;
+                    for (int j = 0; j < jn; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(tr + j);
+                        const float4 qv = *reinterpret_cast<const float4 *>(qrow + j0 + j);
+                        float t;
+                        t = __fsub_rn(qv.x, bv.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                        t = __fsub_rn(qv.y, bv.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                        t = __fsub_rn(qv.z, bv.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                        t = __fsub_rn(qv.w, bv.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    }
+                }
             }
-        } else {
-            for (int j = 0; j < a.d; ++j) {
-                float t = __fsub_rn(qrow[j], __ldg(brow + j));
-                acc = __fadd_rn(acc, __fmul_rn(t, t));
-            }
+            if (lane < nbatch) keys[b0 + lane] = make_key(acc, my_id);
         }
-        keys[i] = make_key(acc, id);
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t id = key_pos(keys[i]);
+            const float *brow = a.base + (size_t)id * a.d;
+            float acc = 0.0f;
+            if ((a.d & 3) == 0) {
+                const float4 *b4 = reinterpret_cast<const float4 *>(brow);
+                for (int j = 0; j < a.d / 4; ++j) {
+                    const float4 bv = __ldg(b4 + j);
+                    float t;
+                    t = __fsub_rn(qrow[4 * j + 0], bv.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    t = __fsub_rn(qrow[4 * j + 1], bv.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    t = __fsub_rn(qrow[4 * j + 2], bv.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                    t = __fsub_rn(qrow[4 * j + 3], bv.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                }
+            } else {
+                for (int j = 0; j < a.d; ++j) {
+                    float t = __fsub_rn(qrow[j], __ldg(brow + j));
+                    acc = __fadd_rn(acc, __fmul_rn(t, t));
+                }
+            }
+            keys[i] = make_key(acc, id);
+        }
     }
     __syncwarp();
     warp_sort_keys_n(keys, n, lane);  // n <= NMAX, NMAX a power of two
@@ -852,23 +907,23 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     lo->total = off + 1024;
 }
 
-template <int GCAP, bool I8, int NMMA, bool EARLY>
+template <int GCAP, bool I8, int NMMA, int MODE>
 cudaError_t launch_tc_one(const TcMaps &maps, const TcArgs &args, size_t smem, int grid,
                           cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<GCAP, I8, NMMA, EARLY>,
+    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<GCAP, I8, NMMA, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    knn_tc_kernel<GCAP, I8, NMMA, EARLY><<<grid, tc_threads(NMMA), smem, stream>>>(maps, args);
+    knn_tc_kernel<GCAP, I8, NMMA, MODE><<<grid, tc_threads(NMMA), smem, stream>>>(maps, args);
     return cudaGetLastError();
 }
 template <int GCAP, bool I8>
 cudaError_t launch_tc_cfg(const TcMaps &maps, const TcArgs &args, size_t smem, int grid, int nmma,
                           bool early, cudaStream_t stream) {
     if (early)
-        return nmma == 2 ? launch_tc_one<GCAP, I8, 2, true>(maps, args, smem, grid, stream)
-                         : launch_tc_one<GCAP, I8, 1, true>(maps, args, smem, grid, stream);
-    return nmma == 2 ? launch_tc_one<GCAP, I8, 2, false>(maps, args, smem, grid, stream)
-                     : launch_tc_one<GCAP, I8, 1, false>(maps, args, smem, grid, stream);
+        return nmma == 2 ? launch_tc_one<GCAP, I8, 2, 1>(maps, args, smem, grid, stream)
+                         : launch_tc_one<GCAP, I8, 1, 1>(maps, args, smem, grid, stream);
+    return nmma == 2 ? launch_tc_one<GCAP, I8, 2, 0>(maps, args, smem, grid, stream)
+                     : launch_tc_one<GCAP, I8, 1, 0>(maps, args, smem, grid, stream);
 }
 
 }  // namespace
@@ -1091,6 +1146,8 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         args.cand = p.cand;
         args.cand_cnt = p.cnt;
         args.cand_tau = p.tau;
+        args.pick_cell = p.pick_cell;
+        args.pick_hist = p.pick_hist;
 
         const int n_items =
             p.g.q_tail0 * p.g.nsplit + (p.g.n_qtiles - p.g.q_tail0) * p.g.ns_tail;
@@ -1100,6 +1157,12 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             if ((pe = launch_tcs(&maps, &args, p.gcap, lo.d16, n_items, num_sms, stream)) !=
                 cudaSuccess)
                 return pe;
+        } else if (p.pick_cell) {
+            const int grid = n_items < num_sms ? n_items : num_sms;
+            const size_t smem = tc_smem_bytes(args.plan);
+            pe = p.i8 ? launch_tc_one<256, true, 2, 2>(maps, args, smem, grid, stream)
+                      : launch_tc_one<256, false, 2, 2>(maps, args, smem, grid, stream);
+            if (pe != cudaSuccess) return pe;
         } else {
             const int grid = n_items < num_sms ? n_items : num_sms;
             const size_t smem = tc_smem_bytes(args.plan);
@@ -1117,10 +1180,12 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         }
         ++*launches;
         if (p.ev3) cudaEventRecord(p.ev3[1], stream);
-        if (p.pick_cell)
+        if (p.pick_cell) {
+            if (!p.streaming) return cudaSuccess;  // the arg-max epilogue wrote the cells itself
             return launch_order_pick(p.cand, p.cnt, p.n_rows, p.gcap, p.g.nsplit,
                                      p.g.q_tail0 * TC_ROWS, p.g.ns_tail, p.pick_cell, p.pick_hist,
                                      stream, launches);
+        }
 
         // ---- re-rank + certificate ----
         RerankArgs ra;
@@ -1158,19 +1223,28 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         const int nmax = p.gcap * splits;
         const int rgrid = (p.n_rows + RR_WARPS - 1) / RR_WARPS;
         const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
-#define LAUNCH_RR(N)                                                                             \
+        // wide rows whose start is 16-byte aligned go through the coalescing path
+        const bool wide = d >= 256 && (d & 3) == 0 && (reinterpret_cast<uintptr_t>(d_base) & 15) == 0;
+        const size_t tbytes = wide ? (size_t)RR_WARPS * 32 * RR_TSTR * sizeof(float) : 0;
+#define LAUNCH_RR1(N, W)                                                                         \
     do {                                                                                         \
-        size_t sm = (size_t)RR_WARPS * N * sizeof(key64_t) + qbytes;                             \
-        if ((pe = cudaFuncSetAttribute(knn_rerank_kernel<N>,                                     \
+        size_t sm = (size_t)RR_WARPS * N * sizeof(key64_t) + qbytes + tbytes;                    \
+        if ((pe = cudaFuncSetAttribute(knn_rerank_kernel<N, W>,                                  \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != \
             cudaSuccess)                                                                         \
             return pe;                                                                           \
-        knn_rerank_kernel<N><<<rgrid, RR_WARPS * 32, sm, stream>>>(ra);                          \
+        knn_rerank_kernel<N, W><<<rgrid, RR_WARPS * 32, sm, stream>>>(ra);                       \
+    } while (0)
+#define LAUNCH_RR(N)                                                                             \
+    do {                                                                                         \
+        if (wide) LAUNCH_RR1(N, true);                                                           \
+        else LAUNCH_RR1(N, false);                                                               \
     } while (0)
         if (nmax <= 256) LAUNCH_RR(256);
         else if (nmax <= 512) LAUNCH_RR(512);
         else if (nmax <= 1024) LAUNCH_RR(1024);
         else LAUNCH_RR(2048);
+#undef LAUNCH_RR1
 #undef LAUNCH_RR
         ++*launches;
         if (p.ev3) cudaEventRecord(p.ev3[2], stream);
@@ -1190,6 +1264,12 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             prep_rows(used_i8, src + (size_t)r0 * d, rows, xq, nullptr, nullptr, false, nullptr, 0);
             Pass pa;
             tc_geom(rows, lo.cells / TC_BN, lo.gcap, num_sms, &pa.g);
+            if (!lo.streaming) {  // arg-max epilogue: one work item per query tile, no base splits
+                pa.g.nsplit = pa.g.ns_tail = 1;
+                pa.g.q_tail0 = pa.g.n_qtiles;
+                pa.g.tiles_per_split = pa.g.tiles_per_split_tail = lo.cells / TC_BN;
+                pa.g.n_slots = (size_t)rows;
+            }
             pa.L_exact = pa.L_inexact = 8;
             pa.gcap = lo.gcap;
             pa.nmma = lo.nmma;

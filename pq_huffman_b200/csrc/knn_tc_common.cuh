@@ -86,6 +86,9 @@ struct TcArgs {
     key64_t *cand;
     int *cand_cnt;
     float *cand_tau;
+    // arg-max mode (cell assignment of the locality order): the column with the best score of
+    // every row and a histogram of those columns, instead of candidate lists
+    int *pick_cell, *pick_hist;
     TcPlan plan;
 };
 
@@ -616,6 +619,79 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
     }
     if (lane == 0 && slow_tiles)
         atomicAdd(const_cast<unsigned long long *>(&args.sc->dbg[2]), (unsigned long long)slow_tiles);
+}
+
+
+// Arg-max flavour of the filter warps: the nearest pivot of every row (knn_order.cu).  The
+// "base" is the pivot set, a sweep is a few dozen tiles, and all that is wanted per row is the
+// column with the best score -- no candidate lists, no thresholds to certify.  Same geometry and
+// barriers as epilogue_warps; the accumulator stage is released as soon as the tile is in
+// registers.  Ties keep the lower column.  One work item per query tile (no base splits).
+template <bool I8>
+__device__ __forceinline__ void epilogue_warps_argmax(const TcArgs &args, int e, int quad, int lane,
+                                                      EpiBars *eb) {
+    typedef Score<I8> S;
+    typedef typename S::T T;
+    const int g = e >> 2;
+    const int row_in_cta = g * 128 + quad * 32 + lane;
+    const uint32_t tmem_row = eb->tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 128);
+    const int n_items = total_items(args);
+    uint32_t gstep = 0;
+    int it_par = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemInfo it = decode_item(args, item);
+        const int t_lo = it.t_lo, t_hi = it.t_hi;
+        const int r = it.qt * TC_ROWS + row_in_cta;
+        T best = S::lowest();
+        int best_col = 0;
+        const int nst = t_hi - t_lo;
+        const int wlen = own_window_len(args, t_lo, t_hi);
+        ItemOrder ord = {t_lo, 0};
+        for (int i = 0; i < nst; ++i) {
+            const uint32_t s = gstep + (uint32_t)i;
+            const int as = (int)(s & 1u);
+            ptx::mbar_wait(&eb->acc_full[as], (s >> 1) & 1u);
+            ptx::tc_fence_after_sync();
+            if (i == 0) {
+                ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
+                ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
+                ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
+            }
+            const int col_base = item_tile(i, ord, wlen, t_lo, t_hi) * TC_BN;
+            const uint32_t tbase = tmem_row + (uint32_t)(as * 256);
+            uint32_t ra[64], rb[64];
+            ptx::tmem_ld_32x32b_x64(tbase, ra);
+            ptx::tmem_ld_32x32b_x64(tbase + 64, rb);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&eb->acc_empty[as]);
+#define PQH_V(q, j) S::from_bits(((q) < 8) ? ra[(q) * 8 + (j)] : rb[((q) - 8) * 8 + (j)])
+#pragma unroll
+            for (int q = 0; q < TC_BN / 8; ++q) {
+                T m = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
+                m = S::max3(m, PQH_V(q, 3), PQH_V(q, 4));
+                m = S::max3(m, PQH_V(q, 5), PQH_V(q, 6));
+                m = S::max2(m, PQH_V(q, 7));
+                if (__any_sync(0xffffffffu, m > best)) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const T v = PQH_V(q, j);
+                        const bool p = v > best && col_base + q * 8 + j < args.nb;
+                        best = p ? v : best;
+                        best_col = p ? col_base + q * 8 + j : best_col;
+                    }
+                }
+            }
+#undef PQH_V
+        }
+        gstep += (uint32_t)nst;
+        it_par ^= 1;
+        if (r < args.n_rows) {
+            args.pick_cell[r] = best_col;
+            atomicAdd(args.pick_hist + best_col, 1);
+        }
+    }
 }
 
 }  // namespace

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sched.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -135,12 +136,13 @@ struct DevBuf {
 };
 
 // ---- pinned staging for pageable host buffers ---------------------------------------------------
-constexpr int STAGE_THREADS = 4;             // helper threads per device and direction
+constexpr int STAGE_THREADS = 8;             // most helper threads per device and direction
 constexpr size_t STAGE_CHUNK = 8u << 20;     // bytes per pinned buffer
 struct Staging {
     void *buf[STAGE_THREADS][2] = {};
     cudaEvent_t ev[STAGE_THREADS][2] = {};
     bool ready = false;
+    int threads = 4;  // helper threads in use: the host cores shared out over the devices
     int init() {
         if (ready) return PQH_OK;
         for (int t = 0; t < STAGE_THREADS; ++t)
@@ -332,6 +334,16 @@ int create_ctx(const int *devices, int n, std::shared_ptr<Context> *out) {
         for (size_t g = 0; g < c->devs.size(); ++g) c->devs[g].comm = comms[g];
         c->nccl = true;
     }
+    {
+        // host threads that copy pageable buffers into the pinned rings: the cores this process
+        // may run on, shared out over the devices (2 .. STAGE_THREADS each)
+        int cores = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+        int per = cores / (int)c->devs.size();
+        per = per < 2 ? 2 : (per > STAGE_THREADS ? STAGE_THREADS : per);
+        for (auto &d : c->devs) d.stage.threads = per;
+    }
     *out = c;
     return PQH_OK;
 }
@@ -433,7 +445,7 @@ int h2d_rows(DeviceCtx &dc, float *dst, const float *src, size_t ld, size_t cols
         return PQH_OK;
     }
     const size_t n_chunks = (n_rows + rows_per_chunk - 1) / rows_per_chunk;
-    const int nt = (int)(n_chunks < (size_t)STAGE_THREADS ? n_chunks : (size_t)STAGE_THREADS);
+    const int nt = (int)(n_chunks < (size_t)dc.stage.threads ? n_chunks : (size_t)dc.stage.threads);
     std::vector<cudaError_t> errs(nt, cudaSuccess);
     auto work = [&](int t) {
         cudaSetDevice(dc.dev);
@@ -480,7 +492,7 @@ int d2h_bytes(DeviceCtx &dc, void *dst, const void *src, size_t bytes) {
     int rc = dc.stage.init();
     if (rc) return rc;
     const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
-    const int nt = (int)(n_chunks < (size_t)STAGE_THREADS ? n_chunks : (size_t)STAGE_THREADS);
+    const int nt = (int)(n_chunks < (size_t)dc.stage.threads ? n_chunks : (size_t)dc.stage.threads);
     std::vector<cudaError_t> errs(nt, cudaSuccess);
     auto work = [&](int t) {
         cudaSetDevice(dc.dev);

@@ -581,31 +581,32 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
 
         const int nst = t_hi - t_lo;
         const int wlen = own_window_len(args, t_lo, t_hi);
-        ItemOrder ord = {t_lo, 0};
+        // the producer wrote the tile order of this item before it loaded anything
+        ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
+        ItemOrder ord;
+        ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
+        ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
         for (int i = 0; i < nst; ++i) {
             const uint32_t s = gstep + (uint32_t)i;
             const int as = (int)(s & 1u);
             const uint32_t acc_ph = (s >> 1) & 1u;
-            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
-            ptx::tc_fence_after_sync();
-            if (i == 0) {
-                ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
-                ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
-                ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
-            }
-            const int t = item_tile(i, ord, wlen, t_lo, t_hi);
-            const uint32_t tbase = tmem_row + (uint32_t)(as * 256);
+            // everything that does not need the accumulator is computed BEFORE the wait: what
+            // follows the barrier flip is on the critical path of the accumulator ring
+            int tile0 = item_tile(i, ord, wlen, t_lo, t_hi) * TC_BN;
+            uint32_t tbase = tmem_row + (uint32_t)(as * 256);
             // id checks are only needed in the tile holding this row's own column and in
             // the (possibly ragged) last tile
-            const int tile0 = t * TC_BN;
-            const bool special = (t == t_hi - 1) || (self >= tile0 && self < tile0 + TC_BN);
+            int special = (tile0 == (t_hi - 1) * TC_BN) || (self >= tile0 && self < tile0 + TC_BN);
+            asm volatile("" : "+r"(tile0), "+r"(tbase), "+r"(special));
+            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
+            ptx::tc_fence_after_sync();
             auto release = [&]() {
                 ptx::tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&eb->acc_empty[as]);
             };
             if (args.debug_mode != 1)
-                filter_tile<GCAP, I8, EARLY>(tbase, tile0, special, ib_hi, self, L, lane,
+                filter_tile<GCAP, I8, EARLY>(tbase, tile0, special != 0, ib_hi, self, L, lane,
                                              args.debug_mode, tau, cnt, list, slow_tiles, release);
             else
                 release();
@@ -646,19 +647,17 @@ __device__ __forceinline__ void epilogue_warps_argmax(const TcArgs &args, int e,
         int best_col = 0;
         const int nst = t_hi - t_lo;
         const int wlen = own_window_len(args, t_lo, t_hi);
-        ItemOrder ord = {t_lo, 0};
+        ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
+        ItemOrder ord;
+        ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
+        ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
         for (int i = 0; i < nst; ++i) {
             const uint32_t s = gstep + (uint32_t)i;
             const int as = (int)(s & 1u);
-            ptx::mbar_wait(&eb->acc_full[as], (s >> 1) & 1u);
-            ptx::tc_fence_after_sync();
-            if (i == 0) {
-                ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
-                ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
-                ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
-            }
             const int col_base = item_tile(i, ord, wlen, t_lo, t_hi) * TC_BN;
             const uint32_t tbase = tmem_row + (uint32_t)(as * 256);
+            ptx::mbar_wait(&eb->acc_full[as], (s >> 1) & 1u);
+            ptx::tc_fence_after_sync();
             uint32_t ra[64], rb[64];
             ptx::tmem_ld_32x32b_x64(tbase, ra);
             ptx::tmem_ld_32x32b_x64(tbase + 64, rb);

@@ -350,7 +350,10 @@ def run_ours(args):
                            "split H2D + ncclAllGather + per-GPU search + D2H into the caller's "
                            "arrays"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": achieved,
+            "roofline": {"bound": "tensor",
+                         # d > 144 takes the streaming kernel (A and B k-blocks through one ring)
+                         "kernel": "knn_tcs_kernel" if d > 144 else "knn_tc_kernel",
+                         "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": f"{peak_src} bf16_tflops_sustained (kernel runs inside a "
                                         "long step)",

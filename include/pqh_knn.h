@@ -69,8 +69,19 @@ void knn_full_thread(int distance_type, int nq, int nb, int d, int k, const floa
  * named by $PQH_DEVICES (comma separated ordinals, default: device 0 only);
  * these calls make it explicit.  Replaces nothing in the reference (it has no
  * device state); they exist so that compute_nn_fast's hundreds of per-block
- * calls (run(), compute_nn_fast.c:556-610) reuse streams, pinned staging and
- * device buffers instead of re-creating them.
+ * calls (run(), compute_nn_fast.c:556-610) reuse streams, pinned staging rings,
+ * NCCL communicators and device buffers instead of re-creating them.
+ *
+ * A context over several devices creates one NCCL communicator per device
+ * (ncclCommInitAll; libnccl.so.2 is resolved at run time).  A host-pointer search
+ * then splits the query rows evenly over the devices; every device uploads 1/G of
+ * the base over its own PCIe link, one in-place ncclAllGather over NVLink
+ * assembles the base on all of them, and each device writes its rows straight into
+ * the caller's arrays.  If NCCL cannot be loaded or initialised, pqh_knn_init
+ * fails with PQH_ECOMM ($PQH_NO_NCCL=1 opts out: every device then receives the
+ * whole base over its own link).
+ *
+ * The $PQH_TC_* tuning knobs are read when a context is created.
  */
 int pqh_knn_init(const int *devices, int n_devices); /* NULL/0: $PQH_DEVICES or {0} */
 void pqh_knn_shutdown(void);
@@ -112,9 +123,15 @@ int pqh_knn_search_rows_ld(int nq_total, int nb, int d, int k, const float *b, l
 /*
  * Device-resident variant for callers that already hold the vectors in HBM
  * (bench.py's device-timed arm, a future GPU loader): all pointers are device
- * pointers on `device`, the call is asynchronous on `stream` (a cudaStream_t
- * passed as void*; NULL = the context's own stream, synchronous).  d_work must
- * point to pqh_knn_workspace_bytes(...) bytes of device scratch.
+ * pointers on `device`; the kernels are launched on `stream` (a cudaStream_t
+ * passed as void*; NULL = the context's own stream).  The call is NOT fully
+ * asynchronous: it synchronises `stream` up to three times (to learn which operand
+ * flavour the data allows, how many rows failed the certificate, and -- rarely --
+ * how many remained after the second pass); with a caller's stream it returns
+ * with the last kernels still in flight, with NULL it returns when the results
+ * are complete.  d_work must point to pqh_knn_workspace_bytes(...) bytes of device
+ * scratch; the figure is bounded in n (candidate lists are kept for one slice of
+ * query rows at a time, $PQH_TC_SLICE_MB, 2 GiB by default).
  */
 long long pqh_knn_workspace_bytes(int nq, int nb, int d, int k);
 int pqh_knn_search_device(int device, int nq_total, int nb, int d, int k, const float *d_b,

@@ -13,10 +13,10 @@ from pq_huffman_b200 import synth, vecs_io
 vecs_io.write_xvecs('/tmp/part.fvecs', synth.sift_like($N, 128), 'f')"
 cd /tmp
 for i in 1 2; do
-  s=$(date +%s%N); $R/pq_huffman_b200/pqh_compute_nn_fast /tmp/part.fvecs /tmp/po_ 16 --temp-file /tmp/pt.vecs | tail -1; e=$(date +%s%N)
+  s=$(date +%s%N); $R/pq_huffman_b200/pqh_compute_nn_fast /tmp/part.fvecs /tmp/po_ 16 --temp-file /tmp/pt.vecs | tail -2 | head -1; e=$(date +%s%N)
   echo "pqh_compute_nn_fast (243 blocks, $N rows, blocks merged on the device) run $i: wall $(( (e - s) / 1000000 )) ms"
 done
-s=$(date +%s%N); $R/pq_huffman_b200/pqh_compute_nn_fast /tmp/part.fvecs /tmp/ph_ 16 --temp-file /tmp/pth.vecs --host-merge | tail -1; e=$(date +%s%N)
+s=$(date +%s%N); $R/pq_huffman_b200/pqh_compute_nn_fast /tmp/part.fvecs /tmp/ph_ 16 --temp-file /tmp/pth.vecs --host-merge | tail -2 | head -1; e=$(date +%s%N)
 echo "pqh_compute_nn_fast --host-merge (243 blocks, $N rows): wall $(( (e - s) / 1000000 )) ms"
 cmp /tmp/po_nn_indices.ivecsl /tmp/ph_nn_indices.ivecsl && cmp /tmp/po_nn_dist.fvecsl /tmp/ph_nn_dist.fvecsl && echo "device merge == host merge ($N rows)"
 s=$(date +%s%N)

@@ -61,18 +61,63 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md).
+
+    Sampled in-process through NVML every few milliseconds (a timed region of a short workload
+    is over before a freshly started `nvidia-smi -lms` prints its first line), one sample taken
+    synchronously when the region starts; `nvidia-smi` is the fallback when NVML cannot be
+    loaded.  The device is found by its PCI bus id, so CUDA_VISIBLE_DEVICES does not matter."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []      # nvidia-smi lines
+        self.samples = []   # NVML: (sm_mhz, power_w, reasons bitmask)
         self.proc = None
         self.gpu = gpu_index
+        self.nvml = None
+        self.handle = None
+        self.smax = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            return True
+        except Exception:
+            self.nvml = None
+            return False
+
+    def _nvml_sample(self):
+        n = self.nvml
+        try:
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            self.samples.append((sm, pw, rs))
+        except Exception:
+            pass
+
+    def _nvml_loop(self):
+        while not self.stop_flag.wait(0.004):
+            self._nvml_sample()
 
     def start(self):
+        if self._nvml_open():
+            self._nvml_sample()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
@@ -87,7 +132,28 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    @staticmethod
+    def _summary(sm, smax, power, reasons, source):
+        # under-load samples: the upper half of the SM clock readings
+        sm = sorted(sm)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm),
+                "reasons": sorted(reasons), "source": source}
+
     def stop(self):
+        if self.nvml is not None:
+            self._nvml_sample()      # one more while the last step is still warm
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            reasons = {name for name, b in bits.items() if any(r & b for _, _, r in self.samples)}
+            return self._summary([s[0] for s in self.samples], self.smax,
+                                 [s[1] for s in self.samples], reasons, "nvml")
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -110,12 +176,7 @@ class ClockSampler:
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        # under-load samples: the upper half of the SM clock readings
-        sm.sort()
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": smax,
-                "power_w_max": max(power) if power else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return self._summary(sm, smax, power, reasons, "nvidia-smi")
 
 
 def config_of(workload, gpus):

@@ -52,12 +52,14 @@ struct OrderOut {
 struct OrderBufs {
     int C;  // cells (= pivots); 0: no locality order
     int *piv_ids, *cell_b, *base_perm, *base_inv, *cell_q, *q_perm, *q_self;
+    int *piv_raw, *piv_group, *group_top;  // pivot numbering: evenly spaced rows, their groups
     int *hist_b, *start_b, *cur_b, *hist_q, *start_q, *cur_q, *qt_start;
 };
 int order_num_cells(int nb);
 size_t order_workspace_bytes(int slice_rows, int nb, int slice_qtiles);
 void order_carve(void *d_work, int slice_rows, int nb, int slice_qtiles, OrderBufs *w);
-cudaError_t launch_order_pivots(const OrderBufs &w, int nb, cudaStream_t stream, int *launches);
+cudaError_t launch_order_pivots(const OrderBufs &w, const float *d_base, int nb, int d,
+                                cudaStream_t stream, int *launches);
 cudaError_t launch_order_pick(const void *cand, const int *cnt, int n_rows, int gcap, int nlists,
                               int tail_row0, int ns_tail, int *cell, int *hist,
                               cudaStream_t stream, int *launches);

@@ -18,10 +18,11 @@
 // re-rank kernel maps them back (base_perm) before it orders ties.
 //
 // The nearest pivot of a row is itself a k = 1 search of the row against the C pivots, so it
-// runs on the tensor cores through the same GEMM + filter kernel (launch_knn_tc drives it:
-// pivot operand, one short sweep per row slice, then order_pick_kernel takes the best entry of
-// every row's candidate list); what is here are the small integer kernels around it: pivot
-// choice, counting sort by cell, inverse permutation, start tile of every query tile.
+// runs on the tensor cores through the same GEMM kernel with an arg-max epilogue (launch_knn_tc
+// drives it: pivot operand, one short sweep per row slice; the streaming kernel keeps candidate
+// lists and order_pick_kernel takes the best entry of every row's); what is here are the small
+// kernels around it: pivot choice and numbering (spatially close cells get neighbouring numbers),
+// counting sort by cell, inverse permutation, start tile of every query tile.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -38,6 +39,86 @@ constexpr int ORD_MIN_CELLS = 512;  // four base tiles: the shortest sweep the f
 __global__ void order_pivot_ids_kernel(int *__restrict__ ids, int C, int nb) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) ids[c] = (int)(((long long)c * 2 + 1) * nb / (2LL * C));
+}
+
+// Numbering of the cells.  A sweep starts with a WINDOW of consecutive base tiles at the query
+// tile's own cell, so what lies next to a cell in the permuted base should be near it in space
+// too.  The pivots are therefore renumbered along a three-level tree: every ORD_GROUP-th pivot
+// stands for a group, every pivot joins the group whose representative is nearest to it, every
+// group likewise joins one of ORD_TOPS top-level representatives, and the cells are numbered by
+// (top, group, original number).  Small, off the tensor cores: C x C/8 x d multiply-adds.
+constexpr int ORD_GROUP = 8, ORD_TOPS = 16;
+
+// out[i] = j minimising |x[ids[i * i_stride]] - x[ids[j * ref_stride]]|^2 over j < n_ref (ties:
+// lowest j).  One warp per i.
+__global__ void __launch_bounds__(256)
+order_nearest_kernel(const float *__restrict__ x, int d, const int *__restrict__ ids, int n,
+                     int i_stride, int ref_stride, int n_ref, int *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float *a = x + (size_t)ids[i * i_stride] * d;
+    float best = __int_as_float(0x7f800000);
+    int bj = 0;
+    for (int j0 = 0; j0 < n_ref; j0 += 8) {  // eight candidates at a time: independent chains
+        const float *b[8];
+        float s[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u < n_ref ? j0 + u : n_ref - 1;
+            b[u] = x + (size_t)ids[j * ref_stride] * d;
+            s[u] = 0.0f;
+        }
+        for (int t = lane; t < d; t += 32) {
+            const float av = a[t];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float df = av - __ldg(b[u] + t);
+                s[u] = fmaf(df, df, s[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (j0 + u < n_ref && s[u] < best) {
+                best = s[u];
+                bj = j0 + u;
+            }
+    }
+    if (lane == 0) out[i] = bj;
+}
+
+// ids_out = ids_in sorted by (top of the pivot's group, group, pivot number); one block, C <= 4096
+__global__ void __launch_bounds__(1024)
+order_rank_cells_kernel(const int *__restrict__ group_of, const int *__restrict__ top_of, int C,
+                        const int *__restrict__ ids_in, int *__restrict__ ids_out) {
+    __shared__ uint32_t key[4096];
+    for (int c = threadIdx.x; c < 4096; c += 1024) {
+        uint32_t k = 0xFFFFFFFFu;
+        if (c < C) {
+            const int g = group_of[c];
+            k = ((uint32_t)top_of[g] << 24) | ((uint32_t)g << 12) | (uint32_t)c;
+        }
+        key[c] = k;
+    }
+    __syncthreads();
+    for (int len = 2; len <= 4096; len <<= 1)
+        for (int inc = len >> 1; inc > 0; inc >>= 1) {
+            for (int t = threadIdx.x; t < 2048; t += 1024) {
+                const int lo = ((t / inc) * (inc << 1)) + (t % inc), hi = lo + inc;
+                const bool up = (lo & len) == 0;
+                const uint32_t a = key[lo], b = key[hi];
+                if ((a > b) == up) {
+                    key[lo] = b;
+                    key[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    for (int r = threadIdx.x; r < C; r += 1024) ids_out[r] = ids_in[key[r] & 0xFFFu];
 }
 
 // cell[r] = position (= pivot number) of the best-scoring entry of row r's candidate lists from
@@ -141,7 +222,12 @@ size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-// 0: no locality order for a base this small (the sweep is too short to matter)
+// Number of cells: about 32 base rows per cell, between 512 and 4096 (the cell assignment is a
+// sweep over the pivots, and 4096 cells are what pays at 1M rows: 244 rows per cell, slow (warp,
+// tile) pairs 33 % -> 0.6 %).  Short sweeps want the small cells: a 100k-row base ran its
+// GEMM + filter in 3.6 ms with 512 cells and in 2.6 ms with 4096, because only cells this small
+// put a row's neighbours into the few tiles its sweep starts with.
+// 0: no locality order for a base this small (the sweep is too short to matter).
 int order_num_cells(int nb) {
     static const int forced = [] {
         const char *e = getenv("PQH_TC_CELLS");  // experiments
@@ -150,14 +236,14 @@ int order_num_cells(int nb) {
     if (nb < 32768) return 0;
     if (forced >= ORD_MIN_CELLS && forced <= ORD_MAX_CELLS) return forced / TC_BN * TC_BN;
     int c = ORD_MIN_CELLS;
-    while (c < ORD_MAX_CELLS && (long long)c * 256 < nb) c *= 2;
+    while (c < ORD_MAX_CELLS && (long long)c * 32 < nb) c *= 2;
     return c;
 }
 
 size_t order_workspace_bytes(int slice_rows, int nb, int slice_qtiles) {
     const int C = order_num_cells(nb);
     size_t b = 0;
-    b += up256((size_t)C * sizeof(int));               // pivot ids
+    b += 4 * up256((size_t)C * sizeof(int));           // pivot ids (raw, renumbered), groups, tops
     b += 3 * up256((size_t)nb * sizeof(int));          // cell_b, base_perm, base_inv
     b += 3 * up256((size_t)slice_rows * sizeof(int));  // cell_q, q_perm, q_self
     b += 6 * up256((size_t)(C + 1) * sizeof(int));     // hist / start / cursor, base and queries
@@ -174,6 +260,9 @@ void order_carve(void *d_work, int slice_rows, int nb, int slice_qtiles, OrderBu
         return r;
     };
     w->piv_ids = static_cast<int *>(take((size_t)w->C * sizeof(int)));
+    w->piv_raw = static_cast<int *>(take((size_t)w->C * sizeof(int)));
+    w->piv_group = static_cast<int *>(take((size_t)w->C * sizeof(int)));
+    w->group_top = static_cast<int *>(take((size_t)w->C * sizeof(int)));
     w->cell_b = static_cast<int *>(take((size_t)nb * sizeof(int)));
     w->base_perm = static_cast<int *>(take((size_t)nb * sizeof(int)));
     w->base_inv = static_cast<int *>(take((size_t)nb * sizeof(int)));
@@ -189,12 +278,30 @@ void order_carve(void *d_work, int slice_rows, int nb, int slice_qtiles, OrderBu
     w->qt_start = static_cast<int *>(take((size_t)slice_qtiles * sizeof(int)));
 }
 
-// pivot rows; clears the base histogram
-cudaError_t launch_order_pivots(const OrderBufs &w, int nb, cudaStream_t stream, int *launches) {
+// pivot rows, numbered along the group tree; clears the base histogram
+cudaError_t launch_order_pivots(const OrderBufs &w, const float *d_base, int nb, int d,
+                                cudaStream_t stream, int *launches) {
+    static const bool flat = [] {
+        const char *e = getenv("PQH_TC_FLAT_CELLS");  // experiments: cells in pivot-row order
+        return e && atoi(e) != 0;
+    }();
     cudaError_t e = cudaMemsetAsync(w.hist_b, 0, 3 * up256((size_t)(w.C + 1) * sizeof(int)), stream);
     if (e != cudaSuccess) return e;
-    order_pivot_ids_kernel<<<(w.C + 127) / 128, 128, 0, stream>>>(w.piv_ids, w.C, nb);
-    ++*launches;
+    const int groups = w.C / ORD_GROUP;
+    if (flat || groups < 2 * ORD_TOPS) {
+        order_pivot_ids_kernel<<<(w.C + 127) / 128, 128, 0, stream>>>(w.piv_ids, w.C, nb);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    order_pivot_ids_kernel<<<(w.C + 127) / 128, 128, 0, stream>>>(w.piv_raw, w.C, nb);
+    order_nearest_kernel<<<(w.C + 7) / 8, 256, 0, stream>>>(d_base, d, w.piv_raw, w.C, 1, ORD_GROUP,
+                                                            groups, w.piv_group);
+    order_nearest_kernel<<<(groups + 7) / 8, 256, 0, stream>>>(
+        d_base, d, w.piv_raw, groups, ORD_GROUP, ORD_GROUP * (groups / ORD_TOPS), ORD_TOPS,
+        w.group_top);
+    order_rank_cells_kernel<<<1, 1024, 0, stream>>>(w.piv_group, w.group_top, w.C, w.piv_raw,
+                                                    w.piv_ids);
+    *launches += 4;
     return cudaGetLastError();
 }
 

@@ -245,7 +245,8 @@ __device__ __forceinline__ void mbar_wait2(uint64_t *b0, uint32_t p0, uint64_t *
 // Steps are numbered over the life of the CTA: B ring stage = step % 4, accumulator stage =
 // step & 1.
 // MODE: 0 = filter, stage released after the filtering; 1 = filter, stage released early;
-// 2 = arg-max (cell assignment of the locality order).
+// 2 = arg-max (cell assignment of the locality order); 4 = mode 1 with cycle accounting in the
+// filter warps (diagnostic builds, -DPQH_TC_PROF).
 template <int GCAP, bool I8, int NMMA, int MODE>
 __global__ void __launch_bounds__(tc_threads(NMMA), 1)
 knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
@@ -404,7 +405,8 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         if constexpr (MODE == 2)
             epilogue_warps_argmax<I8>(args, warp - EPI0, warp & 3, lane, &tail.eb);
         else
-            epilogue_warps<GCAP, I8, MODE == 1>(args, warp - EPI0, warp & 3, lane, &tail.eb);
+            epilogue_warps<GCAP, I8, MODE == 1 || MODE == 4, MODE == 4>(args, warp - EPI0, warp & 3,
+                                                                        lane, &tail.eb);
     }
 
     ptx::tc_fence_before_sync();
@@ -747,6 +749,16 @@ int pick_L(int kcap, bool inexact) {
     if (L < 64) L = 64;
     return L;
 }
+// Integer path: scores are exact, the certificate's only slack is the parity bit of |y|^2 (a
+// non-candidate is at least dist(tau) - 1 away), so a quarter more than the neighbours asked for
+// is enough; a row with ties at its k-th distance goes to the second pass either way.  Measured
+// at L = 20 instead of 24 for k = 16: no row lost, 5 % off short sweeps, 25 % off the re-rank.
+int pick_L_i8(int kcap) {
+    if (env().l_exact > 0) return env().l_exact;
+    const int slack = kcap / 4 > 4 ? kcap / 4 : 4;
+    return (kcap + slack + 3) / 4 * 4;
+}
+
 // List capacity.  The filter checks the count once per tile, after up to TC_BN (128) appends,
 // and a shrink leaves up to L + L/2 entries: L + L/2 + TC_BN must fit.
 int pick_gcap(int L) {
@@ -820,7 +832,7 @@ void tc_geom(int n_rows, int n_btiles, int gcap, int num_sms, TcGeom *g) {
 // exceed $PQH_TC_SLICE_MB (2 GiB by default; a slice is a whole number of rounds of the
 // persistent grid), whatever n is.
 struct TcLayout {
-    int d16, d32, L, L_exact, gcap, nmma, n_btiles;
+    int d16, d32, L, L_exact, L_i8, gcap, nmma, n_btiles;
     bool streaming, order;
     int slice_rows, slice_qtiles;
     size_t scalars, xh_b, fold_b, fold_a, norm_b, norm_q, xq, cand, cnt, tau, fb_rows, order_ws;
@@ -839,6 +851,7 @@ void tc_layout(int n_rows, int nb, int d, int k, int self_join, int num_sms, TcL
     lo->d32 = (d + 31) / 32 * 32;
     lo->L = pick_L(kcap, true);
     lo->L_exact = pick_L(kcap, false);
+    lo->L_i8 = pick_L_i8(kcap);
     lo->gcap = pick_gcap(lo->L);
     lo->streaming = ev.streaming || !resident_fits(lo->d16);
     lo->nmma = lo->streaming ? 1 : ev.nmma;
@@ -919,6 +932,10 @@ cudaError_t launch_tc_one(const TcMaps &maps, const TcArgs &args, size_t smem, i
 template <int GCAP, bool I8>
 cudaError_t launch_tc_cfg(const TcMaps &maps, const TcArgs &args, size_t smem, int grid, int nmma,
                           bool early, cudaStream_t stream) {
+#ifdef PQH_TC_PROF  // diagnostic build: cycle accounting of the filter warps (PQH_TC_DEBUG=3)
+    if (early && nmma == 2 && GCAP == 256 && args.debug_mode == 3)
+        return launch_tc_one<256, I8, 2, 4>(maps, args, smem, grid, stream);
+#endif
     if (early)
         return nmma == 2 ? launch_tc_one<GCAP, I8, 2, 1>(maps, args, smem, grid, stream)
                          : launch_tc_one<GCAP, I8, 1, 1>(maps, args, smem, grid, stream);
@@ -1026,7 +1043,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     // ---- which operand flavour does the data allow?  Integers in [0, 255] whose norms fit the
     //      fold columns take the exact INT8 path; one flag read-back decides ----
     bool used_i8 = false;
-    const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode == 0 || debug_mode == 1) &&
+    const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode == 0 || debug_mode == 1 || debug_mode == 3) &&
                              resident_fits(lo.d32 / 2);
     if (i8_possible) {
         prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d32, nullptr,
@@ -1141,7 +1158,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         args.own_tiles = ev.own_tiles;
         args.kcap = p.kcap;
         args.L_exact = p.L_exact;
-        args.L_inexact = p.L_inexact;
+        args.L_inexact = p.i8 ? p.L_exact : p.L_inexact;  // integer scores are exact
         args.sc = sc;
         args.cand = p.cand;
         args.cand_cnt = p.cnt;
@@ -1305,7 +1322,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     };
     if (lo.order) {
         order_carve(order_ws, lo.slice_rows, nb, lo.slice_qtiles, &ob);
-        if ((e = launch_order_pivots(ob, nb, stream, launches)) != cudaSuccess) return e;
+        if ((e = launch_order_pivots(ob, d_base, nb, d, stream, launches)) != cudaSuccess) return e;
         prep_rows(used_i8, d_base, ob.C, piv_op, nullptr, piv_fold, true, ob.piv_ids, 0);
         if ((e = assign_cells(d_base, nb, ob.cell_b, ob.hist_b)) != cudaSuccess) return e;
         if ((e = launch_order_sort_base(ob, nb, stream, launches)) != cudaSuccess) return e;
@@ -1350,7 +1367,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
             p1.a_rows = (uint64_t)nb;
             p1.q_op_begin = s_begin;
         }
-        p1.L_exact = lo.L_exact;
+        p1.L_exact = used_i8 ? lo.L_i8 : lo.L_exact;
         p1.L_inexact = lo.L;
         p1.gcap = lo.gcap;
         p1.nmma = lo.nmma;
@@ -1402,7 +1419,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     //      rows fail (FP16 cannot resolve this data at all) or when there are only a handful.
     const unsigned n_fb1 = hsc.fb_count;
     if (n_fb1 >= 64 && n_fb1 <= (unsigned)n_rows / 2 && !ev.no_pass2 && debug_mode == 0) {
-        const int L1 = (hsc.inexact && !used_i8) ? lo.L : lo.L_exact;
+        const int L1 = used_i8 ? lo.L_i8 : (hsc.inexact ? lo.L : lo.L_exact);
         int L2 = 4 * L1;
         if (L2 > 192) L2 = 192;
         if (L2 > L1) {
@@ -1503,6 +1520,15 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                     "slices %d\n",
                     (double)hsc.dbg[0], (double)hsc.dbg[1], (double)hsc.dbg[2], n_fb1, lo.nmma,
                     (int)lo.order, n_slices);
+#ifdef PQH_TC_PROF
+        if (debug_mode == 3)
+            fprintf(stderr,
+                    "tc prof: filter warps (cycles summed over warps): wait %.4g (of which idle "
+                    "shrinks %.4g, %.4g of them) | tmem copy %.4g | hot path %.4g | scan+append "
+                    "%.4g | shrinks at capacity %.4g (%.4g lists)\n",
+                    (double)hsc.dbg[3], (double)hsc.dbg[8], (double)hsc.dbg[9], (double)hsc.dbg[4],
+                    (double)hsc.dbg[5], (double)hsc.dbg[6], (double)hsc.dbg[7], (double)hsc.dbg[10]);
+#endif
         cudaEventElapsedTime(&times->ms_prep, evs[0], evs[1]);
         times->ms_gemm = times->ms_rerank = 0.f;
         for (int si = 0; si < n_slices; ++si) {

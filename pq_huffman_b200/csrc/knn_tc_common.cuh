@@ -56,7 +56,7 @@ struct PrepScalars {
     uint32_t i8_reject;    // integer path: bit 0 = a value is not an integer in [0, 255],
                            // bit 1 = |y|^2 beyond the capacity of the fold columns
     unsigned long long cand_total[32];  // candidates re-ranked (spread to avoid contention)
-    unsigned long long dbg[8];          // [0],[1] PQH_TC_DEBUG: MMA-thread cycle counters;
+    unsigned long long dbg[16];         // [0],[1] PQH_TC_DEBUG: MMA-thread cycle counters;
                                         // [2] (warp, tile) pairs that took the slow path
 };
 
@@ -371,6 +371,31 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
     cnt += p ? 1 : 0;
 }
 
+// Cycle accounting of a filter warp (diagnostic builds only, -DPQH_TC_PROF: MODE 4 of
+// knn_tc_kernel): with ON = false every call is empty and the object has no state.
+template <bool ON>
+struct EpiProf {
+    uint32_t t[ON ? 8 : 1];
+    uint32_t last;
+    __device__ __forceinline__ void init() {
+        if constexpr (ON) {
+            for (int i = 0; i < 8; ++i) t[i] = 0;
+            last = (uint32_t)clock();
+        }
+    }
+    __device__ __forceinline__ void lap(int i) {
+        if constexpr (ON) {
+            const uint32_t now = (uint32_t)clock();
+            t[i] += now - last;
+            last = now;
+        }
+    }
+    __device__ __forceinline__ void add(int i, uint32_t v) {
+        if constexpr (ON) t[i] += v;
+    }
+};
+enum { PROF_WAIT = 0, PROF_LD, PROF_HOT, PROF_SCAN, PROF_HARD, PROF_IDLE, PROF_N_IDLE, PROF_N_HARD };
+
 // Epilogue of one accumulator tile for one warp: 32 query rows (one per thread, the TMEM lane
 // it may read) x TC_BN columns starting at TMEM address tbase / base position col_base.
 // The 32 x 128 slice is copied to registers with two 64-column tcgen05.ld in flight together.
@@ -380,20 +405,22 @@ __device__ __forceinline__ void append_if(bool p, key64_t *list, int &cnt, uint3
 //   short K the accumulator hand-offs dominate: one 256 x 128 kind::i8 tile is 640 cycles of MMA
 //   against ~900 cycles of commit / wake-up / release latencies, and the two stages TMEM has room
 //   for cannot hide a filter on top of that.)  Hot path: four independent running maxima with
-//   3-input max give the row maximum (the 128 values have to stay live, so there is no register
-//   room for per-group maxima); one compare with the row's threshold tau and one vote.  Nothing
-//   above tau in any row of the warp (the common case): done.  Slow path: every group of 8
-//   columns is tested (warp-uniform) and the scores above tau are appended, straight from the
-//   registers, with predicated stores.
+//   3-input max, one per 32-column quarter, give the row maximum (the 128 values have to stay
+//   live, so there is no register room for per-group maxima); one compare with the row's
+//   threshold tau and one vote.  Nothing above tau in any row of the warp (the common case):
+//   done.  Slow path: the quarters that hold something (one vote each; usually just one) are
+//   gone through group by group of 8 columns (warp-uniform) and the scores above tau are
+//   appended, straight from the registers, with predicated stores.
 // !EARLY: 16 group maxima level by level, vote, then the flagged groups are re-read from TMEM by
 //   address in one small loop and the stage is released after that (before the scan when at
 //   most two groups are flagged).
 // Either way a list that reached its hard capacity is shrunk (rare).
-template <int GCAP, bool I8, bool EARLY, class Release>
+template <int GCAP, bool I8, bool EARLY, bool PROF, class Release>
 __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool special, int ib_hi,
                                             int self, int L, int lane, int debug_mode,
                                             typename Score<I8>::T &tau, int &cnt, key64_t *list,
-                                            unsigned &slow_tiles, Release release) {
+                                            unsigned &slow_tiles, EpiProf<PROF> &prof,
+                                            Release release) {
     typedef Score<I8> S;
     typedef typename S::T T;
     constexpr int NG = TC_BN / 8;  // groups of 8 columns
@@ -404,6 +431,7 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
 #define PQH_V(q, j) S::from_bits(((q) < 8) ? ra[(q) * 8 + (j)] : rb[((q) - 8) * 8 + (j)])
     if constexpr (EARLY) {
         release();
+        prof.lap(PROF_LD);
         // "special" tiles (ragged last tile, the row's own column): take the forbidden columns
         // out here, once, so that the scan below tests scores only
         if (__any_sync(0xffffffffu, special)) {
@@ -428,22 +456,34 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
             m2 = S::max3(m2, PQH_V(8 + (c >> 3), c & 7), PQH_V(8 + ((c + 1) >> 3), (c + 1) & 7));
             m3 = S::max3(m3, PQH_V(12 + (c >> 3), c & 7), PQH_V(12 + ((c + 1) >> 3), (c + 1) & 7));
         }
-        m0 = S::max3(m0, PQH_V(3, 7), m1);
-        m2 = S::max3(m2, PQH_V(7, 7), m3);
-        const T rm = S::max3(S::max3(m0, m2, PQH_V(11, 7)), PQH_V(15, 7), S::lowest());
-        if (!__any_sync(0xffffffffu, rm > tau) || debug_mode == 2) return;
+        // maxima of the four 32-column quarters (the slow path only scans quarters that hold
+        // something), then of the row
+        m0 = S::max2(m0, PQH_V(3, 7));
+        m1 = S::max2(m1, PQH_V(7, 7));
+        m2 = S::max2(m2, PQH_V(11, 7));
+        m3 = S::max2(m3, PQH_V(15, 7));
+        const T rm = S::max3(S::max3(m0, m1, m2), m3, S::lowest());
+        const bool hot = !__any_sync(0xffffffffu, rm > tau) || debug_mode == 2;
+        prof.lap(PROF_HOT);
+        if (hot) return;
         ++slow_tiles;
+        const T qm[4] = {m0, m1, m2, m3};
 #pragma unroll
-        for (int q = 0; q < NG; ++q) {
-            T m = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
-            m = S::max3(m, PQH_V(q, 3), PQH_V(q, 4));
-            m = S::max3(m, PQH_V(q, 5), PQH_V(q, 6));
-            m = S::max2(m, PQH_V(q, 7));
-            if (__any_sync(0xffffffffu, m > tau)) {
+        for (int Q = 0; Q < 4; ++Q) {
+            if (!__any_sync(0xffffffffu, qm[Q] > tau)) continue;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t bits = (q < 8) ? ra[q * 8 + j] : rb[(q - 8) * 8 + j];
-                    append_if<I8>(S::from_bits(bits) > tau, list, cnt, bits, col_base + q * 8 + j);
+            for (int q = Q * 4; q < Q * 4 + 4; ++q) {
+                T m = S::max3(PQH_V(q, 0), PQH_V(q, 1), PQH_V(q, 2));
+                m = S::max3(m, PQH_V(q, 3), PQH_V(q, 4));
+                m = S::max3(m, PQH_V(q, 5), PQH_V(q, 6));
+                m = S::max2(m, PQH_V(q, 7));
+                if (__any_sync(0xffffffffu, m > tau)) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t bits = (q < 8) ? ra[q * 8 + j] : rb[(q - 8) * 8 + j];
+                        append_if<I8>(S::from_bits(bits) > tau, list, cnt, bits,
+                                      col_base + q * 8 + j);
+                    }
                 }
             }
         }
@@ -509,10 +549,13 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
         }
     }
 #undef PQH_V
+    prof.lap(PROF_SCAN);
     if (cnt > GCAP) __trap();  // list overflow would silently corrupt a neighbouring row's list
     // hard capacity: a tile can append up to TC_BN entries before this check runs again
-    shrink_flagged<GCAP, I8, false>(__ballot_sync(0xffffffffu, cnt > GCAP - TC_BN), L, lane, tau,
-                                    cnt, list);
+    const unsigned full = __ballot_sync(0xffffffffu, cnt > GCAP - TC_BN);
+    shrink_flagged<GCAP, I8, false>(full, L, lane, tau, cnt, list);
+    prof.add(PROF_N_HARD, __popc(full));
+    prof.lap(PROF_HARD);
 }
 
 // Wait for the next accumulator tile.  If some list of the warp has grown past 1.5 L and the
@@ -522,17 +565,22 @@ __device__ __forceinline__ void filter_tile(uint32_t tbase, int col_base, bool s
 // case -- nothing to shrink -- goes straight to the suspending wait, which resumes ~60 cycles
 // after the barrier flips (a non-blocking probe costs ~150 cycles even when the phase is
 // already complete).  Loop conditions are warp-uniform: the body runs full-mask collectives.
-template <int GCAP, bool I8>
+template <int GCAP, bool I8, bool PROF>
 __device__ __forceinline__ void wait_acc_with_idle_shrinks(uint64_t *bar, uint32_t parity, int L,
                                                            int lane, typename Score<I8>::T &tau,
-                                                           int &cnt, key64_t *list) {
+                                                           int &cnt, key64_t *list,
+                                                           EpiProf<PROF> &prof) {
     const int soft = (L + L / 2 < GCAP - TC_BN) ? L + L / 2 : GCAP - TC_BN;
     unsigned need = __ballot_sync(0xffffffffu, cnt > soft);
     while (need != 0 && !__all_sync(0xffffffffu, ptx::mbar_test_wait(bar, parity))) {
+        const uint32_t t0 = PROF ? (uint32_t)clock() : 0u;
         shrink_flagged<GCAP, I8, true>(need & (0u - need), L, lane, tau, cnt, list);
         need = __ballot_sync(0xffffffffu, cnt > soft);
+        prof.add(PROF_IDLE, (uint32_t)clock() - t0);
+        prof.add(PROF_N_IDLE, 1);
     }
     ptx::mbar_wait(bar, parity);
+    prof.lap(PROF_WAIT);
 }
 
 // Barriers and hand-over words the filter warps use, in the shared-memory tail of both kernels.
@@ -549,7 +597,7 @@ struct EpiBars {
 // i.e. 32 query rows, one per lane, and filters every base tile of the sweep for them.
 // Steps are numbered over the whole life of the CTA (gstep): accumulator stage = step & 1,
 // barrier phase = (step >> 1) & 1.
-template <int GCAP, bool I8, bool EARLY>
+template <int GCAP, bool I8, bool EARLY, bool PROF = false>
 __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int quad, int lane,
                                                EpiBars *eb) {
     typedef Score<I8> S;
@@ -562,6 +610,8 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
     uint32_t gstep = 0;
     int it_par = 0;
     unsigned slow_tiles = 0;
+    EpiProf<PROF> prof;
+    prof.init();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ItemInfo it = decode_item(args, item);
         const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
@@ -598,7 +648,8 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
             // the (possibly ragged) last tile
             int special = (tile0 == (t_hi - 1) * TC_BN) || (self >= tile0 && self < tile0 + TC_BN);
             asm volatile("" : "+r"(tile0), "+r"(tbase), "+r"(special));
-            wait_acc_with_idle_shrinks<GCAP, I8>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt, list);
+            wait_acc_with_idle_shrinks<GCAP, I8, PROF>(&eb->acc_full[as], acc_ph, L, lane, tau, cnt,
+                                                       list, prof);
             ptx::tc_fence_after_sync();
             auto release = [&]() {
                 ptx::tc_fence_before_sync();
@@ -606,8 +657,9 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
                 if (lane == 0) ptx::mbar_arrive(&eb->acc_empty[as]);
             };
             if (args.debug_mode != 1)
-                filter_tile<GCAP, I8, EARLY>(tbase, tile0, special != 0, ib_hi, self, L, lane,
-                                             args.debug_mode, tau, cnt, list, slow_tiles, release);
+                filter_tile<GCAP, I8, EARLY, PROF>(tbase, tile0, special != 0, ib_hi, self, L, lane,
+                                                   args.debug_mode, tau, cnt, list, slow_tiles,
+                                                   prof, release);
             else
                 release();
         }
@@ -620,6 +672,12 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
     }
     if (lane == 0 && slow_tiles)
         atomicAdd(const_cast<unsigned long long *>(&args.sc->dbg[2]), (unsigned long long)slow_tiles);
+    if constexpr (PROF) {
+        if (lane == 0)
+            for (int i = 0; i < 8; ++i)
+                atomicAdd(const_cast<unsigned long long *>(&args.sc->dbg[3 + i]),
+                          (unsigned long long)prof.t[i]);
+    }
 }
 
 

@@ -437,9 +437,14 @@ static void write_light(const char *path, const void *data, size_t elem, long lo
     fclose(f);
 }
 
+static double g_init_seconds = 0;
+
 static void *init_device(void *arg) {
     (void)arg;
-    if (pqh_knn_init(NULL, 0) != PQH_OK) {
+    const double t = now_s();
+    int rc = pqh_knn_init(NULL, 0);
+    g_init_seconds = now_s() - t;
+    if (rc != PQH_OK) {
         fprintf(stderr, "pqh_knn_init failed: %s\n", pqh_last_error());
         exit(1);
     }
@@ -723,11 +728,11 @@ int main(int argc, char **argv) {
     memset(&s, 0, sizeof(s));
     pqh_knn_last_stats(&s);
     printf("done: %lld blocks, %lld rows in blocks; read %.3f s, blocks info %.3f s, CUDA context "
-           "+%.3f s, search+merge %.3f s (block rows %.3f s, waiting for the GPU %.3f s, merge "
+           "%.3f s (+%.3f s not hidden), search+merge %.3f s (block rows %.3f s, waiting for the GPU %.3f s, merge "
            "%.3f s; device: h2d %.1f ms, kernels %.1f ms, d2h %.1f ms; %lld rows by tensor cores, "
            "%lld by the exact kernel), export+write %.3f s, total %.3f s\n",
            end > begin ? end - begin : 0LL, rows_in_blocks, t_read - t0, t_part - t_read,
-           t_init - t_part, t_knn - t_init, t_rows, t_wait_gpu, t_merge_only, s.ms_h2d, s.ms_kernels,
+           g_init_seconds, t_init - t_part, t_knn - t_init, t_rows, t_wait_gpu, t_merge_only, s.ms_h2d, s.ms_kernels,
            s.ms_d2h, s.rows_tensor, s.rows_exact, t_end - t_knn, t_end - t0);
     pqh_knn_shutdown();
     printf("context released in %.3f s\n", now_s() - t_end);

@@ -18,3 +18,5 @@ ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel -s
 echo "ncu full rc=$?"; ls -la gpurun_out/r2_knn_tc_i8_sift1m.ncu-rep
 python bench.py --workload sift100k --steps 5 --warmup 3 --no-cpu > gpurun_out/r2_bench_sift100k_n1.json 2>/dev/null; tail -1 gpurun_out/r2_bench_sift100k_n1.json | cut -c1-300
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_n1.json 2>/dev/null; tail -1 gpurun_out/r2_bench_reference_n1.json | cut -c1-300
+bash scripts/cli_wall_1m.sh > gpurun_out/r2_cli_wall_1m.log 2>&1; tail -5 gpurun_out/r2_cli_wall_1m.log | cut -c1-600
+bash scripts/cli_wall_partitioned.sh 1000000 1 > gpurun_out/r2_cli_wall_partitioned.log 2>&1; tail -8 gpurun_out/r2_cli_wall_partitioned.log | cut -c1-600

@@ -66,8 +66,8 @@ cudaError_t launch_order_pick(const void *cand, const int *cnt, int n_rows, int 
 cudaError_t launch_order_sort_base(const OrderBufs &w, int nb, cudaStream_t stream, int *launches);
 cudaError_t launch_order_clear_queries(const OrderBufs &w, cudaStream_t stream);
 cudaError_t launch_order_sort_queries(const OrderBufs &w, int q_begin, int n_rows, int self_join,
-                                      int n_qtiles, cudaStream_t stream, int *launches,
-                                      OrderOut *out);
+                                      int n_qtiles, int own_tiles, cudaStream_t stream,
+                                      int *launches, OrderOut *out);
 cudaError_t launch_order_self_of(const int *d_ids, int n, const int *base_inv, int *d_q_self,
                                  cudaStream_t stream, int *launches);
 

@@ -203,19 +203,38 @@ __global__ void order_qself_kernel(const int *__restrict__ q_ids, int n, const i
     if (r < n) q_self[r] = inv[q_ids[r]];
 }
 
-// qt_start[qt] = first base tile of the cell that query row qt * 256 (permuted order) belongs to
+// qt_start[qt] = window of base tiles at which query tile qt starts its sweep: first tile in the
+// low 24 bits, length in the bits above (own_window_len / item_order in knn_tc_common.cuh).  The
+// window runs from the first tile of the cell of the tile's first row to the last tile of the
+// cell of its last row -- its rows are sorted by cell, so that is where their cell-mates are --
+// but is at least min_tiles and at most ORD_MAX_WINDOW tiles long.  (With all base rows as
+// queries a tile spans a cell or two; a slice of the rows -- one GPU's share -- spreads a tile
+// over many cells: 125k of 1M rows, 8 cells.  A fixed 8-tile window left those rows without their
+// neighbours: 9x the slow (warp, tile) pairs.)
+constexpr int ORD_MAX_WINDOW = 64;
 __global__ void order_qtstart_kernel(const int *__restrict__ q_start, const int *__restrict__ b_start,
-                                     int C, int n_qtiles, int *__restrict__ qt_start) {
+                                     int C, int n_qtiles, int n_rows, int min_tiles,
+                                     int *__restrict__ qt_start) {
     const int qt = blockIdx.x * blockDim.x + threadIdx.x;
     if (qt >= n_qtiles) return;
-    const int r = qt * TC_ROWS;
-    int lo = 0, hi = C;  // largest c with q_start[c] <= r
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (q_start[mid] <= r) lo = mid;
-        else hi = mid;
-    }
-    qt_start[qt] = b_start[lo] / TC_BN;
+    auto cell_of = [&](int r) {  // largest c with q_start[c] <= r
+        int lo = 0, hi = C;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (q_start[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    };
+    const int r0 = qt * TC_ROWS;
+    const int r1 = r0 + TC_ROWS - 1 < n_rows - 1 ? r0 + TC_ROWS - 1 : n_rows - 1;
+    const int c0 = cell_of(r0), c1 = cell_of(r1);
+    const int t0 = b_start[c0] / TC_BN;
+    const int last_row = b_start[c1 + 1] > b_start[c0] ? b_start[c1 + 1] - 1 : b_start[c0];
+    int wlen = last_row / TC_BN - t0 + 1;
+    wlen = wlen < min_tiles ? min_tiles : wlen;
+    wlen = wlen > ORD_MAX_WINDOW ? ORD_MAX_WINDOW : wlen;
+    qt_start[qt] = t0 | (wlen << 24);
 }
 
 size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -335,8 +354,8 @@ cudaError_t launch_order_clear_queries(const OrderBufs &w, cudaStream_t stream) 
 // Self-join: query q is base row q and shares its cell; otherwise cell_q / hist_q were filled by
 // launch_order_pick.
 cudaError_t launch_order_sort_queries(const OrderBufs &w, int q_begin, int n_rows, int self_join,
-                                      int n_qtiles, cudaStream_t stream, int *launches,
-                                      OrderOut *out) {
+                                      int n_qtiles, int own_tiles, cudaStream_t stream,
+                                      int *launches, OrderOut *out) {
     const int *cq = w.cell_q;
     if (self_join) {
         cudaError_t e = launch_order_clear_queries(w, stream);
@@ -354,8 +373,8 @@ cudaError_t launch_order_sort_queries(const OrderBufs &w, int q_begin, int n_row
                                                                      w.q_self);
         ++*launches;
     }
-    order_qtstart_kernel<<<(n_qtiles + 255) / 256, 256, 0, stream>>>(w.start_q, w.start_b, w.C,
-                                                                     n_qtiles, w.qt_start);
+    order_qtstart_kernel<<<(n_qtiles + 255) / 256, 256, 0, stream>>>(
+        w.start_q, w.start_b, w.C, n_qtiles, n_rows, own_tiles, w.qt_start);
     ++*launches;
     out->base_perm = w.base_perm;
     out->base_inv = w.base_inv;

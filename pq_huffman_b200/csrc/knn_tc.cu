@@ -54,7 +54,7 @@ struct TcEnv {
     int order = 1;     // PQH_TC_ORDER: locality order of the sweep (knn_order.cu)
     int nmma = 2;      // PQH_TC_MMA: MMA-issuing threads per CTA, 1 or 2
     int early = 1;     // PQH_TC_EARLY: release the accumulator stage before filtering (0: after)
-    int own_tiles = 8; // PQH_TC_OWN: tiles of the own-cell window a sweep starts with
+    int own_tiles = 8; // PQH_TC_OWN: least number of tiles in the window a sweep starts with
     int l_exact = 0, l_inexact = 0;  // PQH_TC_LEXACT / PQH_TC_LINEXACT: candidates kept per row
     int gcap = 0;      // PQH_TC_GCAP: list capacity, 256 or 512
     int nsplit = 0;    // PQH_TC_NSPLIT: base splits
@@ -301,7 +301,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
                 ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
                 const ItemOrder ord = item_order(args, qt, t_lo, t_hi, my_next);
-                const int wlen = own_window_len(args, t_lo, t_hi);
+                const int wlen = own_window_len(args, qt, t_lo, t_hi);
                 tail.eb.item_w0[it_par] = ord.w0;
                 tail.eb.item_uc[it_par] = ord.uc;
                 ptx::mbar_arrive(&tail.eb.t0_ready);
@@ -953,6 +953,7 @@ void tc_reload_env() {
     e.early = env_int("PQH_TC_EARLY", 1) != 0;
     e.own_tiles = env_int("PQH_TC_OWN", 8);
     if (e.own_tiles < 1) e.own_tiles = 1;
+    if (e.own_tiles > 64) e.own_tiles = 64;
     e.l_exact = env_int("PQH_TC_LEXACT", 0);
     e.l_inexact = env_int("PQH_TC_LINEXACT", 0);
     e.gcap = env_int("PQH_TC_GCAP", 0);
@@ -1155,7 +1156,6 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         args.tiles_per_split = p.g.tiles_per_split;
         args.n_btiles = p.n_btiles;
         args.debug_mode = p.pick_cell ? 0 : debug_mode;
-        args.own_tiles = ev.own_tiles;
         args.kcap = p.kcap;
         args.L_exact = p.L_exact;
         args.L_inexact = p.i8 ? p.L_exact : p.L_inexact;  // integer scores are exact
@@ -1351,8 +1351,8 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
                 if ((e = launch_order_clear_queries(ob, stream)) != cudaSuccess) return e;
                 if ((e = assign_cells(q_slice, rows, ob.cell_q, ob.hist_q)) != cudaSuccess) return e;
             }
-            if ((e = launch_order_sort_queries(ob, s_begin, rows, self_join, p1.g.n_qtiles, stream,
-                                               launches, &oo)) != cudaSuccess)
+            if ((e = launch_order_sort_queries(ob, s_begin, rows, self_join, p1.g.n_qtiles,
+                                               ev.own_tiles, stream, launches, &oo)) != cudaSuccess)
                 return e;
         }
         // query operand of the slice

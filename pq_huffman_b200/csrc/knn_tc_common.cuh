@@ -69,8 +69,9 @@ struct TcArgs {
     const int *row_ids;  // second pass: absolute query id of each row (null: q_begin + row)
     // Locality order (knn_order.cu): operand row p of the base is data row base_perm[p], query
     // row r of this launch is data row q_perm[r].  q_self[r] = position of query r's own vector
-    // in the base operand (self-join; -1 otherwise) and qt_start[qt] = base tile at which query
-    // tile qt starts its sweep (the cell its rows belong to).  All null: natural order.
+    // in the base operand (self-join; -1 otherwise) and qt_start[qt] = window of base tiles with
+    // which query tile qt starts its sweep (the cells its rows belong to): first tile in the low
+    // 24 bits, length above.  All null: natural order.
     const int *q_self;
     const int *qt_start;
     int n_qtiles, nsplit, tiles_per_split, n_btiles;
@@ -80,7 +81,6 @@ struct TcArgs {
     int q_tail0, ns_tail, tiles_per_split_tail;
     int kcap;        // neighbours needed per row (k, or k-1 for a self-join)
     int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
-    int own_tiles;   // locality order: tiles of the own-cell window a sweep starts with
     int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
     const PrepScalars *sc;
     key64_t *cand;
@@ -148,18 +148,19 @@ __host__ __device__ __forceinline__ size_t list_slot(int r, int sp, int tail_row
 struct ItemOrder {
     int w0, uc;
 };
-__device__ __forceinline__ int own_window_len(const TcArgs &a, int t_lo, int t_hi) {
-    const int n = t_hi - t_lo;
-    return a.qt_start ? (n < a.own_tiles ? n : a.own_tiles) : 0;
+__device__ __forceinline__ int own_window_len(const TcArgs &a, int qt, int t_lo, int t_hi) {
+    if (!a.qt_start) return 0;
+    const int n = t_hi - t_lo, w = (int)((uint32_t)a.qt_start[qt] >> 24);
+    return n < w ? n : w;
 }
 // producer side: my_next = where CTA 0's own cyclic sweep continues
 __device__ __forceinline__ ItemOrder item_order(const TcArgs &a, int qt, int t_lo, int t_hi,
                                                 int my_next) {
-    const int n = t_hi - t_lo, wlen = own_window_len(a, t_lo, t_hi);
+    const int n = t_hi - t_lo, wlen = own_window_len(a, qt, t_lo, t_hi);
     ItemOrder o;
     o.w0 = t_lo;
     if (wlen) {
-        int s = a.qt_start[qt];
+        int s = a.qt_start[qt] & 0xffffff;
         if (s < t_lo || s >= t_hi) s = t_lo;  // the cell lies in another base split
         o.w0 = s < t_hi - wlen ? s : t_hi - wlen;
     }
@@ -630,7 +631,7 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
         const int ib_hi = (int)b_hi;
 
         const int nst = t_hi - t_lo;
-        const int wlen = own_window_len(args, t_lo, t_hi);
+        const int wlen = own_window_len(args, qt, t_lo, t_hi);
         // the producer wrote the tile order of this item before it loaded anything
         ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
         ItemOrder ord;
@@ -704,7 +705,7 @@ __device__ __forceinline__ void epilogue_warps_argmax(const TcArgs &args, int e,
         T best = S::lowest();
         int best_col = 0;
         const int nst = t_hi - t_lo;
-        const int wlen = own_window_len(args, t_lo, t_hi);
+        const int wlen = own_window_len(args, it.qt, t_lo, t_hi);
         ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
         ItemOrder ord;
         ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);

@@ -121,7 +121,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 // the slot of item i is reused by item i+2; the producer is at most one ring
                 // (a fraction of a tile) ahead of the MMA, the epilogue at most two tiles behind
                 const ItemOrder ord = item_order(args, qt, t_lo, t_hi, my_next);
-                const int wlen = own_window_len(args, t_lo, t_hi);
+                const int wlen = own_window_len(args, qt, t_lo, t_hi);
                 tail.eb.item_w0[it_par] = ord.w0;
                 tail.eb.item_uc[it_par] = ord.uc;
                 ptx::mbar_arrive(&tail.eb.t0_ready);

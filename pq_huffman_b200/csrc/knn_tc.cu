@@ -62,6 +62,7 @@ struct TcEnv {
     int debug = 0;     // PQH_TC_DEBUG: 1 = MMA only, 2 = no slow path (timing experiments),
                        // 3 = normal run + counters printed
     int streaming = 0; // PQH_TC_STREAM=1: streaming kernel for every d
+    int dynamic = 1;   // PQH_TC_DYN=0: work items round robin instead of on demand
     int slice_mb = 2048;  // PQH_TC_SLICE_MB: candidate-list scratch per row slice
     bool loaded = false;
 };
@@ -296,14 +297,23 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         if (ptx::elect_one()) {
             int stage = 0, it_par = 0, my_next = 0;
             uint32_t ph = 0, a_ph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = blockIdx.x;;) {
+                // the MMAs of the previous item are done: the query tile may be overwritten and
+                // every consumer has seen the previous flip of t0_ready
+                ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
+                if (item >= n_items) {
+                    tail.eb.item_id[it_par] = -1;
+                    ptx::mbar_arrive(&tail.eb.t0_ready);
+                    break;
+                }
+                const int following = next_item(args, item);
                 const ItemInfo it = decode_item(args, item);
                 const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
-                ptx::mbar_wait(&tail.a_empty, a_ph ^ 1);
                 const ItemOrder ord = item_order(args, qt, t_lo, t_hi, my_next);
                 const int wlen = own_window_len(args, qt, t_lo, t_hi);
                 tail.eb.item_w0[it_par] = ord.w0;
                 tail.eb.item_uc[it_par] = ord.uc;
+                tail.eb.item_id[it_par] = item;
                 ptx::mbar_arrive(&tail.eb.t0_ready);
                 ptx::mbar_arrive_expect_tx(&tail.a_full, plan.a_bytes);
                 for (int s = 0; s < plan.nseg; ++s) {
@@ -337,6 +347,7 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                         ph ^= 1;
                     }
                 }
+                item = following;
             }
         }
     } else if (warp < EPI0) {
@@ -349,7 +360,9 @@ knn_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             long long t_wait = 0;
             const bool prof = args.debug_mode != 0;
             const long long t_begin = prof ? clock64() : 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int it_par = 0;; it_par ^= 1) {
+                const int item = take_item(&tail.eb, it_par);
+                if (item < 0) break;
                 const ItemInfo it = decode_item(args, item);
                 const int nst = it.t_hi - it.t_lo;
                 ptx::mbar_wait(&tail.a_full, a_ph);
@@ -963,6 +976,7 @@ void tc_reload_env() {
     e.check_eps = env_int("PQH_TC_CHECK_EPS", 0);
     e.debug = env_int("PQH_TC_DEBUG", 0);
     e.streaming = env_int("PQH_TC_STREAM", 0) != 0;
+    e.dynamic = env_int("PQH_TC_DYN", 1) != 0;
     e.slice_mb = env_int("PQH_TC_SLICE_MB", 2048);
     if (e.slice_mb < 64) e.slice_mb = 64;
     e.loaded = true;
@@ -1156,6 +1170,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         args.tiles_per_split = p.g.tiles_per_split;
         args.n_btiles = p.n_btiles;
         args.debug_mode = p.pick_cell ? 0 : debug_mode;
+        args.dynamic = (ev.dynamic && !p.streaming) ? 1 : 0;
         args.kcap = p.kcap;
         args.L_exact = p.L_exact;
         args.L_inexact = p.i8 ? p.L_exact : p.L_inexact;  // integer scores are exact
@@ -1169,6 +1184,9 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         const int n_items =
             p.g.q_tail0 * p.g.nsplit + (p.g.n_qtiles - p.g.q_tail0) * p.g.ns_tail;
         cudaError_t pe;
+        if (args.dynamic &&
+            (pe = cudaMemsetAsync(&sc->work_next, 0, sizeof(uint32_t), stream)) != cudaSuccess)
+            return pe;
         if (p.ev3) cudaEventRecord(p.ev3[0], stream);
         if (p.streaming) {
             if ((pe = launch_tcs(&maps, &args, p.gcap, lo.d16, n_items, num_sms, stream)) !=

@@ -51,6 +51,8 @@ struct PrepScalars {
     uint32_t inexact;      // some fp16(sigma*x) != sigma*x
     uint32_t fb_count;     // rows that failed the certificate
     uint32_t tile_cursor;  // base tile most recently started by CTA 0 (L2-friendly order)
+    uint32_t work_next;    // work items handed out beyond the first one of every CTA (reset to 0
+                           // before each launch)
     uint32_t eps_ratio_bits;  // PQH_TC_CHECK_EPS: max |S'_tensor - S'_fp64| / eps (float bits)
     uint32_t fb2_count;    // rows that failed the certificate of the second pass
     uint32_t i8_reject;    // integer path: bit 0 = a value is not an integer in [0, 255],
@@ -81,6 +83,7 @@ struct TcArgs {
     int q_tail0, ns_tail, tiles_per_split_tail;
     int kcap;        // neighbours needed per row (k, or k-1 for a self-join)
     int debug_mode;  // timing experiments only: 1 = epilogue does not read TMEM, 2 = no slow path
+    int dynamic;     // work items are handed out by a counter (sc->work_next) instead of round robin
     int L_exact, L_inexact;  // candidates kept per row (data exactly representable in fp16 / not)
     const PrepScalars *sc;
     key64_t *cand;
@@ -590,7 +593,27 @@ struct EpiBars {
     uint64_t t0_ready;  // producer -> epilogue: the order of the next item is written
     uint32_t tmem_base;
     int item_w0[2], item_uc[2];  // tile order of the current / next work item (ItemOrder)
+    int item_id[2];              // ... and which item it is (-1: no more work)
 };
+
+// Work items of a CTA.  The producer thread decides: the first item of CTA b is item b; after
+// that either every gridDim-th item (round robin) or -- args.dynamic -- the next one nobody has
+// taken yet, from a counter in global memory.  Items differ in how long they take (slow tiles,
+// shrinks), and with a fixed share of ~27 items per CTA the slowest CTA of a 1M-row search ran
+// 7 % longer than the average one; handing the items out on demand ends all CTAs within one
+// (short, last) item of each other.  The producer asks for the following item when it starts
+// one, so the atomic's latency is hidden behind a whole sweep; everyone else learns the item
+// from eb->item_id when the t0_ready barrier flips.
+__device__ __forceinline__ int next_item(const TcArgs &a, int item) {
+    if (!a.dynamic) return item + (int)gridDim.x;
+    return (int)gridDim.x +
+           (int)atomicAdd(&const_cast<PrepScalars *>(a.sc)->work_next, 1u);
+}
+// consumer side: the item of this round, -1 when the CTA is done
+__device__ __forceinline__ int take_item(EpiBars *eb, int it_par) {
+    ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
+    return *reinterpret_cast<volatile int *>(&eb->item_id[it_par]);
+}
 
 // The filter warps of one CTA: filter warp e (0 .. 7) owns TMEM lane quadrant `quad` (= its
 // warp index & 3: the quadrant the hardware lets it read; four consecutive warps cover the
@@ -613,7 +636,9 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
     unsigned slow_tiles = 0;
     EpiProf<PROF> prof;
     prof.init();
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        const int item = take_item(eb, it_par);
+        if (item < 0) break;
         const ItemInfo it = decode_item(args, item);
         const int qt = it.qt, sp = it.sp, t_lo = it.t_lo, t_hi = it.t_hi;
         const int r = qt * TC_ROWS + row_in_cta;
@@ -633,7 +658,6 @@ __device__ __forceinline__ void epilogue_warps(const TcArgs &args, int e, int qu
         const int nst = t_hi - t_lo;
         const int wlen = own_window_len(args, qt, t_lo, t_hi);
         // the producer wrote the tile order of this item before it loaded anything
-        ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
         ItemOrder ord;
         ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
         ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);
@@ -698,7 +722,9 @@ __device__ __forceinline__ void epilogue_warps_argmax(const TcArgs &args, int e,
     const int n_items = total_items(args);
     uint32_t gstep = 0;
     int it_par = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        const int item = take_item(eb, it_par);
+        if (item < 0) break;
         const ItemInfo it = decode_item(args, item);
         const int t_lo = it.t_lo, t_hi = it.t_hi;
         const int r = it.qt * TC_ROWS + row_in_cta;
@@ -706,7 +732,6 @@ __device__ __forceinline__ void epilogue_warps_argmax(const TcArgs &args, int e,
         int best_col = 0;
         const int nst = t_hi - t_lo;
         const int wlen = own_window_len(args, it.qt, t_lo, t_hi);
-        ptx::mbar_wait(&eb->t0_ready, (uint32_t)it_par);
         ItemOrder ord;
         ord.w0 = *reinterpret_cast<volatile int *>(&eb->item_w0[it_par]);
         ord.uc = *reinterpret_cast<volatile int *>(&eb->item_uc[it_par]);

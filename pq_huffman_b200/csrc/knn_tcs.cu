@@ -114,7 +114,14 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
         if (ptx::elect_one()) {
             int stage = 0, it_par = 0, my_next = 0;
             uint32_t ph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = blockIdx.x;; item += gridDim.x) {
+                if (item >= n_items) {
+                    // consumers saw the flip of the last item long ago (their last accumulator
+                    // wait is behind the last loads, which are behind that flip)
+                    tail.eb.item_id[it_par] = -1;
+                    ptx::mbar_arrive(&tail.eb.t0_ready);
+                    break;
+                }
                 const ItemInfo it = decode_item(args, item);
                 const int qt = it.qt, t_lo = it.t_lo, t_hi = it.t_hi;
                 const int arow = args.q_op_begin + qt * TC_ROWS;
@@ -124,6 +131,7 @@ knn_tcs_kernel(const __grid_constant__ TcMaps maps, const TcArgs args, int d16) 
                 const int wlen = own_window_len(args, qt, t_lo, t_hi);
                 tail.eb.item_w0[it_par] = ord.w0;
                 tail.eb.item_uc[it_par] = ord.uc;
+                tail.eb.item_id[it_par] = item;
                 ptx::mbar_arrive(&tail.eb.t0_ready);
                 it_par ^= 1;
                 for (int ti = 0; ti < t_hi - t_lo; ++ti) {

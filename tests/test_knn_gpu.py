@@ -198,6 +198,8 @@ KNOBS = [
     dict(PQH_TC_STREAM=1, PQH_TC_ORDER=0),
     dict(PQH_TC_I8=0, PQH_TC_MMA=1),
     dict(PQH_TC_SLICE_MB=64),
+    dict(PQH_TC_DYN=0),
+    dict(PQH_TC_DYN=0, PQH_TC_MMA=1, PQH_TC_I8=0),
 ]
 
 
@@ -219,9 +221,10 @@ def _knob_cases(oracle):
 @pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a[7:]}={b}" for a, b in k.items()))
 def test_kernel_configurations_stay_exact(tc_env, oracle, knobs):
     """Every selectable configuration of the tensor-core path -- one or two MMA issuers, stage
-    release before or after the filtering, locality order on or off, the streaming kernel forced
-    on a small d, small row slices -- must produce the oracle's answer: the knobs only decide how
-    fast.  (Defaults: two issuers, early release, locality order.)"""
+    release before or after the filtering, locality order on or off, work items on demand or round
+    robin, the streaming kernel forced on a small d, small row slices -- must produce the oracle's
+    answer: the knobs only decide how fast.  (Defaults: two issuers, early release, locality
+    order, items on demand.)"""
     c = _knob_cases(oracle)
     tc_env(**knobs)
     got = knn.knn_full_thread(c["x"], None, 17)

@@ -63,6 +63,9 @@ struct TcEnv {
                        // 3 = normal run + counters printed
     int streaming = 0; // PQH_TC_STREAM=1: streaming kernel for every d
     int dynamic = 1;   // PQH_TC_DYN=0: work items round robin instead of on demand
+    int wide_d = 64;   // PQH_TC_WIDE_D: re-rank rows of at least this many floats are fetched by
+                       // the whole warp and handed to their lanes through shared memory
+                       // (measured: d = 128 6.3 -> 4.9 ms at 1M rows, d = 96 k = 32 38 -> 25 ms at 2M)
     int slice_mb = 2048;  // PQH_TC_SLICE_MB: candidate-list scratch per row slice
     bool loaded = false;
 };
@@ -459,11 +462,12 @@ struct RerankArgs {
     uint32_t *fb_count;
 };
 
-// WIDE (large d, rows 16-byte aligned): a lane still owns one candidate and sums its d terms in
+// WIDE (d >= 64, rows 16-byte aligned): a lane still owns one candidate and sums its d terms in
 // index order, but the candidate rows are FETCHED by the whole warp -- 256 contiguous bytes of
 // two rows per load instruction -- and handed to their lanes through a shared-memory tile.  With
-// one scattered 16-byte load per lane (the narrow path) a d = 960 re-rank is bound by the rate of
-// sector requests (32 different rows per instruction), not by bytes.
+// one scattered 16-byte load per lane (the narrow path) the re-rank is bound by the rate of
+// sector requests (32 different rows per instruction), not by bytes: d = 960 213 -> 59 ms,
+// d = 128 6.3 -> 4.9 ms at 1M rows.
 constexpr int RR_DC = 64;        // floats of a row per tile chunk
 constexpr int RR_TSTR = RR_DC + 4;  // tile row stride: 16-byte aligned, conflict-free LDS.128
 
@@ -977,6 +981,7 @@ void tc_reload_env() {
     e.debug = env_int("PQH_TC_DEBUG", 0);
     e.streaming = env_int("PQH_TC_STREAM", 0) != 0;
     e.dynamic = env_int("PQH_TC_DYN", 1) != 0;
+    e.wide_d = env_int("PQH_TC_WIDE_D", 64);
     e.slice_mb = env_int("PQH_TC_SLICE_MB", 2048);
     if (e.slice_mb < 64) e.slice_mb = 64;
     e.loaded = true;
@@ -1259,7 +1264,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
         const int rgrid = (p.n_rows + RR_WARPS - 1) / RR_WARPS;
         const size_t qbytes = (size_t)RR_WARPS * d * sizeof(float);
         // wide rows whose start is 16-byte aligned go through the coalescing path
-        const bool wide = d >= 256 && (d & 3) == 0 && (reinterpret_cast<uintptr_t>(d_base) & 15) == 0;
+        const bool wide = d >= ev.wide_d && (d & 3) == 0 && (reinterpret_cast<uintptr_t>(d_base) & 15) == 0;
         const size_t tbytes = wide ? (size_t)RR_WARPS * 32 * RR_TSTR * sizeof(float) : 0;
 #define LAUNCH_RR1(N, W)                                                                         \
     do {                                                                                         \

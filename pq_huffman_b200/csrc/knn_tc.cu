@@ -118,13 +118,34 @@ prep_rows_kernel(const float *__restrict__ x, int n, int d, int d16, __half *__r
     __half *hr = xh + (size_t)row * d16;
     double acc = 0.0;
     bool inexact = false;
-    for (int i = lane; i < d16; i += 32) {
-        float v = i < d ? xr[i] : 0.0f;
-        float s = v * sigma;  // exact: power-of-two scale
-        __half h = __float2half_rn(s);
-        if (__half2float(h) != s) inexact = true;
-        hr[i] = h;
-        acc += (double)v * (double)v;
+    if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        // four consecutive elements per lane: 16-byte loads, 8-byte stores (d16 is a multiple of 16)
+        for (int i4 = lane; i4 < d16 / 4; i4 += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * i4 < d) v = __ldg(reinterpret_cast<const float4 *>(xr) + i4);
+            const float s0 = v.x * sigma, s1 = v.y * sigma, s2 = v.z * sigma, s3 = v.w * sigma;
+            const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+            if (__low2float(h01) != s0 || __high2float(h01) != s1 || __low2float(h23) != s2 ||
+                __high2float(h23) != s3)
+                inexact = true;
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&h01);
+            pk.y = *reinterpret_cast<const uint32_t *>(&h23);
+            reinterpret_cast<uint2 *>(hr)[i4] = pk;
+            acc += (double)v.x * (double)v.x;
+            acc += (double)v.y * (double)v.y;
+            acc += (double)v.z * (double)v.z;
+            acc += (double)v.w * (double)v.w;
+        }
+    } else {
+        for (int i = lane; i < d16; i += 32) {
+            float v = i < d ? xr[i] : 0.0f;
+            float s = v * sigma;  // exact: power-of-two scale
+            __half h = __float2half_rn(s);
+            if (__half2float(h) != s) inexact = true;
+            hr[i] = h;
+            acc += (double)v * (double)v;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (__any_sync(0xffffffffu, inexact) && lane == 0) atomicOr(&sc->inexact, 1u);
@@ -190,14 +211,38 @@ prep_rows_i8_kernel(const float *__restrict__ x, int n, int d, int d32, uint8_t 
     uint8_t *o = out ? out + (size_t)row * d32 : nullptr;
     double acc = 0.0;
     bool bad = false;
-    for (int i = lane; i < d32; i += 32) {
-        const float v = i < d ? xr[i] : 0.0f;
-        const int iv = (int)v;
-        if (!(v >= 0.0f && v <= 255.0f) || (float)iv != v) bad = true;
-        uint8_t b = 0;
-        if (i < d) b = as_base ? (uint8_t)(int8_t)(iv - 128) : (uint8_t)iv;
-        if (o) o[i] = b;
-        acc += (double)v * (double)v;
+    if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        // four consecutive elements per lane: 16-byte loads, 4-byte stores (d32 is a multiple of 32)
+        const int sub = as_base ? 128 : 0;
+        for (int i4 = lane; i4 < d32 / 4; i4 += 32) {
+            const bool in = 4 * i4 < d;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) v = __ldg(reinterpret_cast<const float4 *>(xr) + i4);
+            const int i0 = (int)v.x, i1 = (int)v.y, i2 = (int)v.z, i3 = (int)v.w;
+            if (!(v.x >= 0.0f && v.x <= 255.0f) || (float)i0 != v.x) bad = true;
+            if (!(v.y >= 0.0f && v.y <= 255.0f) || (float)i1 != v.y) bad = true;
+            if (!(v.z >= 0.0f && v.z <= 255.0f) || (float)i2 != v.z) bad = true;
+            if (!(v.w >= 0.0f && v.w <= 255.0f) || (float)i3 != v.w) bad = true;
+            uint32_t pk = 0;
+            if (in)
+                pk = ((uint32_t)(i0 - sub) & 0xffu) | (((uint32_t)(i1 - sub) & 0xffu) << 8) |
+                     (((uint32_t)(i2 - sub) & 0xffu) << 16) | (((uint32_t)(i3 - sub) & 0xffu) << 24);
+            if (o) reinterpret_cast<uint32_t *>(o)[i4] = pk;
+            acc += (double)v.x * (double)v.x;
+            acc += (double)v.y * (double)v.y;
+            acc += (double)v.z * (double)v.z;
+            acc += (double)v.w * (double)v.w;
+        }
+    } else {
+        for (int i = lane; i < d32; i += 32) {
+            const float v = i < d ? xr[i] : 0.0f;
+            const int iv = (int)v;
+            if (!(v >= 0.0f && v <= 255.0f) || (float)iv != v) bad = true;
+            uint8_t b = 0;
+            if (i < d) b = as_base ? (uint8_t)(int8_t)(iv - 128) : (uint8_t)iv;
+            if (o) o[i] = b;
+            acc += (double)v * (double)v;
+        }
     }
     for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
     unsigned flags = __any_sync(0xffffffffu, bad) ? 1u : 0u;

@@ -199,6 +199,7 @@ KNOBS = [
     dict(PQH_TC_I8=0, PQH_TC_MMA=1),
     dict(PQH_TC_SLICE_MB=64),
     dict(PQH_TC_DYN=0),
+    dict(PQH_TC_WIDE_D=4096),
     dict(PQH_TC_DYN=0, PQH_TC_MMA=1, PQH_TC_I8=0),
 ]
 

@@ -16,7 +16,10 @@ $B > gpurun_out/r2_bench_short2.json 2> gpurun_out/r2_bench_short2.err &&
 ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel -s 5 -c 1 -f \
     -o gpurun_out/r2_knn_tc_i8_sift1m $B > gpurun_out/r2_ncu_i8.log 2>&1
 echo "ncu full rc=$?"; ls -la gpurun_out/r2_knn_tc_i8_sift1m.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:knn_rerank_kernel -s 2 -c 1 -f \
+    -o gpurun_out/r2_knn_rerank_sift1m $B > gpurun_out/r2_ncu_rerank_sift.log 2>&1
+echo "ncu rerank rc=$?"
 python bench.py --workload sift100k --steps 5 --warmup 3 --no-cpu > gpurun_out/r2_bench_sift100k_n1.json 2>/dev/null; tail -1 gpurun_out/r2_bench_sift100k_n1.json | cut -c1-300
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_n1.json 2>/dev/null; tail -1 gpurun_out/r2_bench_reference_n1.json | cut -c1-300
 bash scripts/cli_wall_1m.sh > gpurun_out/r2_cli_wall_1m.log 2>&1; tail -5 gpurun_out/r2_cli_wall_1m.log | cut -c1-600
-bash scripts/cli_wall_partitioned.sh 1000000 1 > gpurun_out/r2_cli_wall_partitioned.log 2>&1; tail -8 gpurun_out/r2_cli_wall_partitioned.log | cut -c1-600
+sleep 5; bash scripts/cli_wall_partitioned.sh 1000000 1 > gpurun_out/r2_cli_wall_partitioned.log 2>&1; tail -8 gpurun_out/r2_cli_wall_partitioned.log | cut -c1-600

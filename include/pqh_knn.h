@@ -25,6 +25,8 @@
 #ifndef PQH_KNN_H_
 #define PQH_KNN_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -35,6 +37,7 @@ extern "C" {
 #define PQH_ECUDA (-3)   /* CUDA runtime / driver failure */
 #define PQH_ENOMEM (-4)  /* host or device allocation failed */
 #define PQH_ECOMM (-5)   /* multi-GPU exchange failed */
+#define PQH_ENOTORDER (-6) /* pqh_sort_edges: the comparator is not an order on this data */
 
 /*
  * Replaces: Yael knn_full_thread, called at compute_nn_fast.c:478-481 (dead
@@ -199,6 +202,35 @@ int pqh_knn_dataset_search_block_merge(int slot, int m, const int *row_ids, int 
                                        long long ticket);
 int pqh_knn_heaps_export(void *image, unsigned *ids, float *dists);
 void pqh_knn_heaps_release(void);
+
+/*
+ * The graph's first consumer: mst_builder turns the two output files into
+ * N*k records {int32 source, int32 target, float dist} (mst_edge_t, mst.h:12-16) and sorts them
+ * with libc qsort -- by distance before Kruskal's pass (mst.c:175 with mst_dist_comparator,
+ * mst.c:15-26: distances closer than 1e-9 count as equal) and, for the forest's edges, by source
+ * (mst.c:214, mst_source_comparator, mst.c:28-32).  glibc's qsort is a stable merge sort, so
+ * where the comparator is an order the result is "ascending, equal keys in input order"; that is
+ * what the device computes (least-significant-digit radix sort with order-keeping scatters,
+ * edge_sort.cu).
+ *
+ *   pqh_sort_edges    sorts n such records in place (host memory).  PQH_SORT_BY_DIST is only
+ *                     taken when the reference comparator IS an order on the data -- no NaN, and
+ *                     no two different distances closer than 1e-9; otherwise nothing is changed
+ *                     and PQH_ENOTORDER is returned (the caller keeps its own sort).
+ *   pqh_qsort_edges   qsort's prototype, for mst.c compiled with -Dqsort=pqh_qsort_edges (no
+ *                     source change): arrays of at least PQH_EDGE_SORT_MIN
+ *                     12-byte records whose comparator answers a few probe records the way one
+ *                     of mst.c's two does go to pqh_sort_edges; every other call -- other record
+ *                     sizes, the per-row sorts of mst.c:134, PQH_ENOTORDER -- IS qsort.  A device
+ *                     failure ends the process with exit(1) like knn_full_thread; there is no
+ *                     silent CPU path for a sort the device was asked to do.
+ */
+#define PQH_SORT_BY_DIST 0
+#define PQH_SORT_BY_SOURCE 1
+#define PQH_EDGE_SORT_MIN 65536
+int pqh_sort_edges(long long n, void *edges, int mode);
+void pqh_qsort_edges(void *base, size_t n, size_t size,
+                     int (*compar)(const void *, const void *));
 
 /*
  * Counters of the last search on this thread's context, for tests and

@@ -28,6 +28,8 @@ EXPORTS = (
     "pqh_knn_heaps_release",
     "pqh_knn_host_alloc",
     "pqh_knn_host_free",
+    "pqh_sort_edges",
+    "pqh_qsort_edges",
 )
 
 
@@ -114,6 +116,10 @@ def load():
     lib.pqh_knn_host_alloc.restype = C.c_void_p
     lib.pqh_knn_host_free.argtypes = [C.c_void_p]
     lib.pqh_knn_host_free.restype = None
+    lib.pqh_sort_edges.argtypes = [C.c_longlong, vp, C.c_int]
+    lib.pqh_sort_edges.restype = C.c_int
+    lib.pqh_qsort_edges.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
+    lib.pqh_qsort_edges.restype = None
     del fp
     _lib = lib
     return lib

@@ -1,6 +1,8 @@
 // kernels.h -- host-callable launchers of the kNN kernels (internal).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <cstdint>
 #include <stddef.h>
 
 #include <vector>
@@ -70,6 +72,11 @@ cudaError_t launch_order_sort_queries(const OrderBufs &w, int q_begin, int n_row
                                       int *launches, OrderOut *out);
 cudaError_t launch_order_self_of(const int *d_ids, int n, const int *base_inv, int *d_q_self,
                                  cudaStream_t stream, int *launches);
+
+// ---- edge_sort.cu (stable sort of the graph's edge records for the MST builder) ----
+size_t edge_sort_workspace_bytes(size_t n);
+cudaError_t launch_edge_sort(const void *d_in, void *d_out, size_t n, int mode, void *d_work,
+                             uint32_t *d_flags, cudaStream_t stream, int *launches);
 
 // ---- knn_tcs.cu (streaming kernel for large d) ----
 cudaError_t launch_tcs(const void *maps, const void *args, int gcap, int d16, int n_items,

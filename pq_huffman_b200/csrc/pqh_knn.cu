@@ -1340,6 +1340,74 @@ int pqh_knn_last_fallback_rows(int *rows, int capacity) {
     return n;
 }
 
+// ---- the graph's first consumer: edge sorts of the MST builder ----------------
+int pqh_sort_edges(long long n, void *edges, int mode) {
+    if (n < 0 || (n > 0 && !edges) || (mode != PQH_SORT_BY_DIST && mode != PQH_SORT_BY_SOURCE))
+        return fail(PQH_EINVAL, "bad edge sort n=%lld mode=%d", n, mode);
+    if (n > 0xffffffffll) return fail(PQH_EINVAL, "edge sort takes at most 2^32 - 1 records");
+    if (n < 2) return PQH_OK;
+    std::shared_ptr<Context> ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    DeviceCtx &dc = ctx->devs[0];
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[0]);
+    CU_TRY(cudaSetDevice(dc.dev));
+    const size_t bytes = (size_t)n * 12;
+    if ((rc = dc.base.ensure(bytes))) return rc;
+    if ((rc = dc.queries.ensure(bytes))) return rc;
+    if ((rc = dc.work.ensure(pqh::edge_sort_workspace_bytes((size_t)n) + 256))) return rc;
+    // 12-byte records travel as rows of three 4-byte words
+    if ((rc = h2d_rows(dc, static_cast<float *>(dc.base.p), static_cast<const float *>(edges), 3, 3,
+                       (size_t)n)))
+        return rc;
+    uint32_t *d_flags = static_cast<uint32_t *>(dc.work.p);
+    int launches = 0;
+    CU_TRY(pqh::launch_edge_sort(dc.base.p, dc.queries.p, (size_t)n, mode,
+                                 static_cast<char *>(dc.work.p) + 256, d_flags, dc.stream,
+                                 &launches));
+    uint32_t flags = 0;
+    CU_TRY(cudaMemcpyAsync(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, dc.stream));
+    CU_TRY(cudaStreamSynchronize(dc.stream));
+    if (mode == PQH_SORT_BY_DIST && flags)
+        return fail(PQH_ENOTORDER,
+                    "edge sort not taken: %s (the reference comparator is not an order on this "
+                    "data; the records were left as they were)",
+                    (flags & 1u) ? "a distance is NaN" : "two different distances are closer than 1e-9");
+    return d2h_bytes(dc, edges, dc.queries.p, bytes);
+}
+
+void pqh_qsort_edges(void *base, size_t n, size_t size,
+                     int (*compar)(const void *, const void *)) {
+    struct Rec {
+        int source, target;
+        float dist;
+    };
+    if (size == sizeof(Rec) && n >= (size_t)PQH_EDGE_SORT_MIN && compar) {
+        // Which of mst.c's two comparators is this?  A few probe records tell them apart (and
+        // anything that answers differently stays with libc).
+        const Rec lo_d = {1, 3, 0.0f}, hi_d = {0, 2, 1.0f};      // less by dist, greater by source
+        const Rec eq_a = {5, 7, 2.0f}, eq_b = {9, 1, 2.0f};      // same dist, different source
+        const Rec sm_a = {4, 1, 2.0f}, sm_b = {4, 8, 3.0f};      // same source, different dist
+        const Rec nx_a = {0, 0, 1.0f}, nx_b = {0, 0, 1.0000001f};  // next float up: 1.2e-7 apart
+        int mode = -1;
+        if (compar(&lo_d, &hi_d) < 0 && compar(&hi_d, &lo_d) > 0 && compar(&eq_a, &eq_b) == 0 &&
+            compar(&nx_a, &nx_b) < 0 && compar(&sm_a, &sm_b) < 0)
+            mode = PQH_SORT_BY_DIST;
+        else if (compar(&lo_d, &hi_d) > 0 && compar(&hi_d, &lo_d) < 0 && compar(&sm_a, &sm_b) == 0 &&
+                 compar(&eq_a, &eq_b) < 0)
+            mode = PQH_SORT_BY_SOURCE;
+        if (mode >= 0) {
+            const int rc = pqh_sort_edges((long long)n, base, mode);
+            if (rc == PQH_OK) return;
+            if (rc != PQH_ENOTORDER) {
+                fprintf(stderr, "libpqh_knn: pqh_qsort_edges failed: %s\n", g_err.c_str());
+                exit(1);
+            }
+        }
+    }
+    qsort(base, n, size, compar);
+}
+
 void knn_full_thread(int distance_type, int nq, int nb, int d, int k, const float *b,
                      const float *v, const float *b_weights, int *assign, float *dis,
                      int n_thread) {

@@ -189,3 +189,21 @@ def heaps_export(n, k, want_image=True):
 
 def heaps_release():
     _lib.load().pqh_knn_heaps_release()
+
+
+EDGE = np.dtype([("source", "<i4"), ("target", "<i4"), ("dist", "<f4")])   # mst_edge_t, mst.h:12-16
+SORT_BY_DIST, SORT_BY_SOURCE = 0, 1
+ENOTORDER = -6
+
+
+def sort_edges(edges, mode=SORT_BY_DIST):
+    """In-place stable sort of EDGE records on the device, the order mst.c:175 / :214 get from
+    qsort.  Returns False (records untouched) when the reference's distance comparator is not an
+    order on this data (PQH_ENOTORDER)."""
+    lib = _lib.load()
+    assert edges.dtype == EDGE and edges.flags.c_contiguous
+    rc = lib.pqh_sort_edges(edges.shape[0], edges.ctypes.data, mode)
+    if rc == ENOTORDER:
+        return False
+    _check(rc)
+    return True

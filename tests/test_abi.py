@@ -75,3 +75,33 @@ def test_argument_validation_needs_no_gpu():
     assert rc == -1
     assert lib.pqh_knn_set_algo(77) == -1
     assert lib.pqh_knn_workspace_bytes(1000, 1000, 16, 9) > 0
+
+
+def test_qsort_shaped_entry_is_qsort_for_what_it_does_not_take():
+    """pqh_qsort_edges (mst.c built with -Dqsort=pqh_qsort_edges) only takes over large arrays of
+    12-byte edge records; anything else -- here 4-byte ints, and a short array of edge records --
+    is sorted by libc, GPU or not."""
+    lib = _lib.load()
+    CMP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+    def int_cmp(a, b):
+        x, y = C.cast(a, C.POINTER(C.c_int))[0], C.cast(b, C.POINTER(C.c_int))[0]
+        return (x > y) - (x < y)
+
+    v = np.random.default_rng(0).integers(-1000, 1000, 500).astype(np.int32)
+    w = v.copy()
+    lib.pqh_qsort_edges(w.ctypes.data, w.size, 4, C.cast(CMP(int_cmp), C.c_void_p))
+    assert np.array_equal(w, np.sort(v))
+
+    e = np.zeros(300, dtype=knn.EDGE)
+    e["dist"] = np.random.default_rng(1).integers(0, 50, 300).astype(np.float32)
+    e["source"] = np.arange(300)
+
+    def dist_cmp(a, b):
+        x = C.cast(a + 8, C.POINTER(C.c_float))[0]
+        y = C.cast(b + 8, C.POINTER(C.c_float))[0]
+        return (x > y) - (x < y)
+
+    s = e.copy()
+    lib.pqh_qsort_edges(s.ctypes.data, s.size, 12, C.cast(CMP(dist_cmp), C.c_void_p))
+    assert np.all(np.diff(s["dist"]) >= 0) and sorted(s["source"]) == list(range(300))

@@ -493,3 +493,40 @@ def test_device_side_merge_follows_the_reference_heap_rules(oracle):
         assert list(ids_out[r]) == [int(v) for v in ei]
         assert np.array_equal(dists_out[r].view(np.uint32),
                               np.array(ed, dtype=np.float32).view(np.uint32))
+
+
+def _random_case(seed):
+    """One seeded shape around the limits of the locality order: a base just below / above the
+    size from which cells are used (32768), row slices of it as queries (a tile then spans many
+    cells: the sweep window is sized per tile), distinct queries, small and large k, d on either
+    side of the widths the kernels switch at (64: warp-wide re-rank fetches; 144: streaming)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([32767, 32768, 33000, 40000, 50001, 65536]))
+    d = int(rng.choice([8, 24, 63, 64, 96, 128, 144, 148, 200]))
+    k = int(rng.choice([1, 2, 9, 17, 33, 65]))
+    gen = [synth.sift_like, synth.deep_like, synth.uniform][int(rng.integers(0, 3))]
+    mode = ["self", "slice", "distinct"][int(rng.integers(0, 3))]
+    return n, d, k, gen, mode, rng
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_around_the_locality_order(oracle, seed):
+    n, d, k, gen, mode, rng = _random_case(seed)
+    x = gen(n, d, seed=seed)
+    if seed % 4 == 0:
+        x = synth.with_duplicates_and_ties(x, n_dups=50, n_ties=50)
+    rows = n
+    if mode == "self":
+        assert_rows_equal(knn.knn_full_thread(x, None, k), oracle.knn(x, None, k))
+    elif mode == "slice":
+        lo = int(rng.integers(0, n - 3000))
+        rows = int(rng.integers(1, 3000))
+        exp = oracle.knn_rows(x, None, k, lo, lo + rows)
+        assert_rows_equal(knn.search_rows(x, None, k, lo, lo + rows), exp)
+    else:
+        rows = int(rng.integers(1, 2500))
+        v = gen(rows, d, seed=seed + 100)
+        assert_rows_equal(knn.knn_full_thread(x, v, k), oracle.knn(x, v, k))
+    kcap = k - (mode != "distinct")          # neighbours asked for beyond the row itself
+    if 1 <= kcap <= 64 and rows >= 256:
+        assert knn.last_stats()["rows_tensor"] > 0

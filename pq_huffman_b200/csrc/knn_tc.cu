@@ -1108,7 +1108,7 @@ cudaError_t launch_knn_tc(const float *d_base, const float *d_queries, int q_row
     // ---- which operand flavour does the data allow?  Integers in [0, 255] whose norms fit the
     //      fold columns take the exact INT8 path; one flag read-back decides ----
     bool used_i8 = false;
-    const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode == 0 || debug_mode == 1 || debug_mode == 3) &&
+    const bool i8_possible = ev.i8 && !lo.streaming && (debug_mode >= 0 && debug_mode <= 3) &&
                              resident_fits(lo.d32 / 2);
     if (i8_possible) {
         prep_rows_i8_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(d_base, nb, d, lo.d32, nullptr,

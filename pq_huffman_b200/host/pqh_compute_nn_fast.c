@@ -218,6 +218,95 @@ static void parallel(int nt, par_fn fn, void *arg) {
     free(th);
 }
 
+/* ---- the same with threads that stay: for the stage that forks once per block.  (Creating
+ * and joining 15 threads took longer than finding a block's rows: 1.4-1.9 ms per block against
+ * the ~0.3 ms the search itself needs -- as long as one block's search on the GPU.)  A pool
+ * belongs to ONE calling thread. ---- */
+typedef struct pool_s pool_t;
+typedef struct {
+    pool_t *pool;
+    int t;
+} pool_worker_t;
+struct pool_s {
+    int nt; /* threads including the caller */
+    pthread_t *th;
+    pool_worker_t *workers;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_start, cv_done;
+    par_fn fn;
+    void *arg;
+    unsigned long generation;
+    int pending, stop;
+};
+
+static void *pool_entry(void *p) {
+    pool_worker_t *w = (pool_worker_t *)p;
+    pool_t *pl = w->pool;
+    unsigned long seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&pl->mu);
+        while (pl->generation == seen && !pl->stop) pthread_cond_wait(&pl->cv_start, &pl->mu);
+        if (pl->stop) {
+            pthread_mutex_unlock(&pl->mu);
+            return NULL;
+        }
+        seen = pl->generation;
+        par_fn fn = pl->fn;
+        void *arg = pl->arg;
+        pthread_mutex_unlock(&pl->mu);
+        fn(w->t, pl->nt, arg);
+        pthread_mutex_lock(&pl->mu);
+        if (--pl->pending == 0) pthread_cond_signal(&pl->cv_done);
+        pthread_mutex_unlock(&pl->mu);
+    }
+}
+
+static void pool_init(pool_t *pl, int nt) {
+    memset(pl, 0, sizeof(*pl));
+    pl->nt = nt < 1 ? 1 : nt;
+    pthread_mutex_init(&pl->mu, NULL);
+    pthread_cond_init(&pl->cv_start, NULL);
+    pthread_cond_init(&pl->cv_done, NULL);
+    pl->th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)pl->nt);
+    pl->workers = (pool_worker_t *)malloc(sizeof(pool_worker_t) * (size_t)pl->nt);
+    for (int t = 1; t < pl->nt; ++t) {
+        pl->workers[t].pool = pl;
+        pl->workers[t].t = t;
+        pthread_create(pl->th + t, NULL, pool_entry, pl->workers + t);
+    }
+}
+
+static void pool_run(pool_t *pl, par_fn fn, void *arg) {
+    if (pl->nt > 1) {
+        pthread_mutex_lock(&pl->mu);
+        pl->fn = fn;
+        pl->arg = arg;
+        pl->pending = pl->nt - 1;
+        ++pl->generation;
+        pthread_cond_broadcast(&pl->cv_start);
+        pthread_mutex_unlock(&pl->mu);
+    }
+    fn(0, pl->nt, arg);
+    if (pl->nt > 1) {
+        pthread_mutex_lock(&pl->mu);
+        while (pl->pending > 0) pthread_cond_wait(&pl->cv_done, &pl->mu);
+        pthread_mutex_unlock(&pl->mu);
+    }
+}
+
+static void pool_destroy(pool_t *pl) {
+    pthread_mutex_lock(&pl->mu);
+    pl->stop = 1;
+    pthread_cond_broadcast(&pl->cv_start);
+    pthread_mutex_unlock(&pl->mu);
+    for (int t = 1; t < pl->nt; ++t) pthread_join(pl->th[t], NULL);
+    free(pl->th);
+    free(pl->workers);
+    pthread_cond_destroy(&pl->cv_start);
+    pthread_cond_destroy(&pl->cv_done);
+    pthread_mutex_destroy(&pl->mu);
+}
+
 /* ---- heaps of all rows ---- */
 typedef struct {
     slot_t *heaps;
@@ -299,11 +388,12 @@ static void block_rows_part(int t, int nt, void *arg) {
                                             a->prefix_len, a->ids + r0);
 }
 
-static long long block_rows(int nt, const pqh_partition_t *part, const float *cols, long long n,
-                            long long block, long long prefix_block, int prefix_len, int *ids,
-                            long long *counts) {
+static long long block_rows(pool_t *pool, const pqh_partition_t *part, const float *cols,
+                            long long n, long long block, long long prefix_block, int prefix_len,
+                            int *ids, long long *counts) {
     rows_arg_t a = {part, cols, n, block, prefix_block, prefix_len, ids, counts};
-    parallel(nt, block_rows_part, &a);
+    const int nt = pool->nt;
+    pool_run(pool, block_rows_part, &a);
     long long m = counts[0];
     for (int t = 1; t < nt; ++t) {
         memmove(ids + m, ids + n * t / nt, sizeof(int) * (size_t)counts[t]);
@@ -400,6 +490,8 @@ static void *device_thread(void *arg) {
 static void *rows_thread(void *arg) {
     pipeline_t *pl = (pipeline_t *)arg;
     long long *counts = (long long *)malloc(sizeof(long long) * (size_t)pl->threads);
+    pool_t pool;
+    pool_init(&pool, pl->threads);
     for (long long b = pl->begin; b < pl->end; ++b) {
         ring_slot_t *s = pl->ring + (b - pl->begin) % pl->ring_len;
         pthread_mutex_lock(&pl->mu);
@@ -408,8 +500,8 @@ static void *rows_thread(void *arg) {
         const double tr = now_s();
         const long long pass_first =
             pl->begin + (b - pl->begin) / pl->blocks_on_pass * pl->blocks_on_pass;
-        s->m = block_rows(pl->threads, pl->part, pl->cols, pl->n, b, pass_first, pl->prefix_len,
-                          s->ids, counts);
+        s->m = block_rows(&pool, pl->part, pl->cols, pl->n, b, pass_first, pl->prefix_len, s->ids,
+                          counts);
         s->k1 = (int)(s->m - 1 < pl->k ? s->m - 1 : pl->k) + 1;
         if (pl->blocks_stat) fprintf(pl->blocks_stat, "%d ", (int)s->m);
         pl->t_rows += now_s() - tr;
@@ -418,6 +510,7 @@ static void *rows_thread(void *arg) {
         pthread_cond_broadcast(&pl->cv);
         pthread_mutex_unlock(&pl->mu);
     }
+    pool_destroy(&pool);
     free(counts);
     return NULL;
 }

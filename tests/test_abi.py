@@ -105,3 +105,15 @@ def test_qsort_shaped_entry_is_qsort_for_what_it_does_not_take():
     s = e.copy()
     lib.pqh_qsort_edges(s.ctypes.data, s.size, 12, C.cast(CMP(dist_cmp), C.c_void_p))
     assert np.all(np.diff(s["dist"]) >= 0) and sorted(s["source"]) == list(range(300))
+
+
+def test_workspace_is_bounded_in_the_number_of_rows():
+    """pqh_knn_workspace_bytes needs no device: candidate lists are kept for one slice of query
+    rows at a time ($PQH_TC_SLICE_MB, 2 GiB by default), so a Deep10M-sized search asks for
+    operands + one slice, not for 41 GB of lists (round 1)."""
+    w1 = knn.workspace_bytes(1_000_000, 1_000_000, 128, 17)
+    w10 = knn.workspace_bytes(10_000_000, 10_000_000, 96, 33)
+    assert 0 < w1 <= 4 * 2**30
+    assert 0 < w10 <= 8 * 2**30
+    # the lists do not grow with n beyond the slice budget: 10x the rows, far less than 10x the bytes
+    assert w10 < 4 * w1

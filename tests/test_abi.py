@@ -117,3 +117,26 @@ def test_workspace_is_bounded_in_the_number_of_rows():
     assert 0 < w10 <= 8 * 2**30
     # the lists do not grow with n beyond the slice budget: 10x the rows, far less than 10x the bytes
     assert w10 < 4 * w1
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_edge_sort_without_a_gpu_fails_loudly():
+    """A sort that pqh_qsort_edges takes (large array of edge records, comparator answering like
+    mst_dist_comparator) is the device's job: without a device the process ends with a message
+    and exit(1), it does not quietly sort on the CPU."""
+    code = r'''
+import ctypes as C, numpy as np
+from pq_huffman_b200 import _lib, knn
+lib = _lib.load()
+CMP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+def dist_cmp(a, b):
+    x = C.cast(a + 8, C.POINTER(C.c_float))[0]; y = C.cast(b + 8, C.POINTER(C.c_float))[0]
+    d = np.float32(x) - np.float32(y)
+    return 0 if abs(float(d)) < 1e-9 else (-1 if d < 0 else 1)
+e = np.zeros(70000, dtype=knn.EDGE); e["dist"] = np.arange(70000, dtype=np.float32)[::-1]
+lib.pqh_qsort_edges(e.ctypes.data, e.size, 12, C.cast(CMP(dist_cmp), C.c_void_p))
+print("sorted on the CPU")
+'''
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert p.returncode == 1 and "sorted on the CPU" not in p.stdout
+    assert "pqh_qsort_edges failed" in p.stderr

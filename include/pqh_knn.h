@@ -233,6 +233,21 @@ void pqh_qsort_edges(void *base, size_t n, size_t size,
                      int (*compar)(const void *, const void *));
 
 /*
+ * The estimator's joint code histograms (nn_huffman_estimator.c:69-107,
+ * collect_stats_at_kth_nn), for the neighbour ranks [nn_first, nn_first + nn_count) at once:
+ * stats[(j * m + i) * k_star * k_star + a * k_star + b] = number of vectors v whose neighbour of
+ * rank nn_first + j is known (index != (unsigned)-1) and that have code a in sub-quantiser i
+ * while that neighbour has code b; num_known[j] = how many vectors had a known neighbour of
+ * that rank (the function's return value).  pq_codes is uint8[n x m] (pq_indices.bvecsl),
+ * nn_indices uint32[n x num_nn] (nn_indices.ivecsl), k_star <= 256.  The counts are integers, so
+ * the doubles are exactly the reference's whatever the order of accumulation.  The function is
+ * static in the reference: the binding is the four-line change INTEGRATION.md shows.
+ */
+int pqh_nn_joint_histograms(long long n, int m, int k_star, int num_nn,
+                            const unsigned char *pq_codes, const unsigned *nn_indices,
+                            int nn_first, int nn_count, double *stats, long long *num_known);
+
+/*
  * Counters of the last search on this thread's context, for tests and
  * bench.py: how the rows were resolved and how many kernels were launched.
  */

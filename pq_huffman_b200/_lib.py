@@ -30,6 +30,7 @@ EXPORTS = (
     "pqh_knn_host_free",
     "pqh_sort_edges",
     "pqh_qsort_edges",
+    "pqh_nn_joint_histograms",
 )
 
 
@@ -120,6 +121,9 @@ def load():
     lib.pqh_sort_edges.restype = C.c_int
     lib.pqh_qsort_edges.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
     lib.pqh_qsort_edges.restype = None
+    lib.pqh_nn_joint_histograms.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int,
+                                            C.c_int, vp, vp]
+    lib.pqh_nn_joint_histograms.restype = C.c_int
     del fp
     _lib = lib
     return lib

@@ -78,6 +78,12 @@ size_t edge_sort_workspace_bytes(size_t n);
 cudaError_t launch_edge_sort(const void *d_in, void *d_out, size_t n, int mode, void *d_work,
                              uint32_t *d_flags, cudaStream_t stream, int *launches);
 
+// ---- nn_stats.cu (joint code histograms of the graph for the estimator) ----
+cudaError_t launch_nn_histograms(const void *d_pq, const void *d_nn, long long n, int m, int k_star,
+                                 int num_nn, int nn_first, int nn_count, uint32_t *d_cnt,
+                                 unsigned long long *d_known, uint32_t *d_flags, double *d_out,
+                                 cudaStream_t stream, int *launches);
+
 // ---- knn_tcs.cu (streaming kernel for large d) ----
 cudaError_t launch_tcs(const void *maps, const void *args, int gcap, int d16, int n_items,
                        int num_sms, cudaStream_t stream);

@@ -1408,6 +1408,63 @@ void pqh_qsort_edges(void *base, size_t n, size_t size,
     qsort(base, n, size, compar);
 }
 
+int pqh_nn_joint_histograms(long long n, int m, int k_star, int num_nn,
+                            const unsigned char *pq_codes, const unsigned *nn_indices,
+                            int nn_first, int nn_count, double *stats, long long *num_known) {
+    if (n < 0 || m <= 0 || k_star <= 0 || k_star > 256 || num_nn <= 0 || nn_first < 0 ||
+        nn_count <= 0 || nn_first + nn_count > num_nn || !stats || !num_known ||
+        (n > 0 && (!pq_codes || !nn_indices)))
+        return fail(PQH_EINVAL, "bad histogram request n=%lld m=%d k*=%d nn=[%d,%d) of %d", n, m,
+                    k_star, nn_first, nn_first + nn_count, num_nn);
+    std::shared_ptr<Context> ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    DeviceCtx &dc = ctx->devs[0];
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu[0]);
+    CU_TRY(cudaSetDevice(dc.dev));
+    const size_t pq_bytes = (size_t)n * m, nn_bytes = (size_t)n * num_nn * sizeof(unsigned);
+    const size_t total = (size_t)nn_count * m * k_star * k_star;
+    const size_t pq_pad = (pq_bytes + 255) & ~(size_t)255;
+    if ((rc = dc.base.ensure(pq_pad + nn_bytes + 256))) return rc;
+    if ((rc = dc.queries.ensure(total * sizeof(double)))) return rc;
+    if ((rc = dc.work.ensure(total * sizeof(uint32_t) + (size_t)nn_count * 8 + 512))) return rc;
+    char *d_pq = static_cast<char *>(dc.base.p), *d_nn = d_pq + pq_pad;
+    // byte and word matrices travel through the staging rings as rows of 4-byte words
+    if (n > 0) {
+        if (pq_bytes % 4 == 0) {
+            if ((rc = h2d_rows(dc, reinterpret_cast<float *>(d_pq),
+                               reinterpret_cast<const float *>(pq_codes), 1, 1, pq_bytes / 4)))
+                return rc;
+        } else {
+            CU_TRY(cudaMemcpyAsync(d_pq, pq_codes, pq_bytes, cudaMemcpyHostToDevice, dc.stream));
+        }
+        if ((rc = h2d_rows(dc, reinterpret_cast<float *>(d_nn),
+                           reinterpret_cast<const float *>(nn_indices), (size_t)num_nn,
+                           (size_t)num_nn, (size_t)n)))
+            return rc;
+    }
+    char *w = static_cast<char *>(dc.work.p);
+    uint32_t *d_flags = reinterpret_cast<uint32_t *>(w);
+    unsigned long long *d_known = reinterpret_cast<unsigned long long *>(w + 256);
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(w + 256 + (((size_t)nn_count * 8 + 255) & ~(size_t)255));
+    int launches = 0;
+    CU_TRY(pqh::launch_nn_histograms(d_pq, d_nn, n, m, k_star, num_nn, nn_first, nn_count, d_cnt,
+                                     d_known, d_flags, static_cast<double *>(dc.queries.p),
+                                     dc.stream, &launches));
+    uint32_t flags = 0;
+    std::vector<unsigned long long> known((size_t)nn_count);
+    CU_TRY(cudaMemcpyAsync(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, dc.stream));
+    CU_TRY(cudaMemcpyAsync(known.data(), d_known, (size_t)nn_count * 8, cudaMemcpyDeviceToHost,
+                           dc.stream));
+    CU_TRY(cudaStreamSynchronize(dc.stream));
+    if (flags)
+        return fail(PQH_EINVAL, "histograms: %s",
+                    (flags & 1u) ? "a neighbour index is not a row of the data set"
+                                 : "a PQ code is not below k_star");
+    for (int j = 0; j < nn_count; ++j) num_known[j] = (long long)known[(size_t)j];
+    return d2h_bytes(dc, stats, dc.queries.p, total * sizeof(double));
+}
+
 void knn_full_thread(int distance_type, int nq, int nb, int d, int k, const float *b,
                      const float *v, const float *b_weights, int *assign, float *dis,
                      int n_thread) {

@@ -207,3 +207,21 @@ def sort_edges(edges, mode=SORT_BY_DIST):
         return False
     _check(rc)
     return True
+
+
+def nn_joint_histograms(pq_codes, nn_indices, k_star=256, nn_first=0, nn_count=None):
+    """(stats float64[nn_count, m, k_star, k_star], num_known int64[nn_count]): what
+    collect_stats_at_kth_nn (nn_huffman_estimator.c:69-107) computes for each neighbour rank."""
+    lib = _lib.load()
+    pq = np.ascontiguousarray(pq_codes, dtype=np.uint8)
+    nn = np.ascontiguousarray(nn_indices).view(np.uint32)
+    n, m = pq.shape
+    num_nn = nn.shape[1]
+    assert nn.shape[0] == n
+    if nn_count is None:
+        nn_count = num_nn - nn_first
+    stats = np.empty((nn_count, m, k_star, k_star), dtype=np.float64)
+    known = np.empty(nn_count, dtype=np.int64)
+    _check(lib.pqh_nn_joint_histograms(n, m, k_star, num_nn, pq.ctypes.data, nn.ctypes.data,
+                                       nn_first, nn_count, stats.ctypes.data, known.ctypes.data))
+    return stats, known

@@ -64,3 +64,21 @@ def single_block_result(assign, dis, num_nn):
         out_i[r] = idx
         out_d[r] = dst
     return out_i, out_d
+
+
+def joint_histograms(pq_codes, nn_indices, k_star, nn_index):
+    """collect_stats_at_kth_nn (nn_huffman_estimator.c:69-107): for every vector whose neighbour of
+    rank nn_index is known (index != (vector_id_t)-1) and every sub-quantiser i,
+    stats[i][code of the vector][code of the neighbour] += 1.  Returns (stats float64[m, k*, k*],
+    number of vectors with a known neighbour)."""
+    pq = np.asarray(pq_codes, dtype=np.uint8)
+    nn = np.asarray(nn_indices).view(np.uint32)
+    n, m = pq.shape
+    col = nn[:, nn_index]
+    known = col != np.uint32(0xFFFFFFFF)
+    src = pq[known].astype(np.int64)
+    dst = pq[col[known].astype(np.int64)].astype(np.int64)
+    stats = np.zeros((m, k_star, k_star), dtype=np.float64)
+    for i in range(m):
+        np.add.at(stats[i], (src[:, i], dst[:, i]), 1.0)
+    return stats, int(known.sum())

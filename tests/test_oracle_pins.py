@@ -85,3 +85,29 @@ def test_reference_cli_with_oracle(tmp_path, oracle, gen, n, d, k):
     exp_i, exp_d = ref_semantics.single_block_result(a, dist, k)
     assert np.array_equal(got_i, exp_i)
     assert np.array_equal(got_d.view(np.uint32), exp_d.view(np.uint32))
+
+
+def test_histogram_restatement_matches_the_reference_function():
+    """tests/ref_semantics.joint_histograms (the checker of pqh_nn_joint_histograms) against the
+    reference's own collect_stats_at_kth_nn, which is static in nn_huffman_estimator.c and
+    reached through oracle/ref_est_shim.c (the source included where it lies)."""
+    import ctypes as C
+    path = os.path.join(oracle_ffi.REF_DIR, "libref_est.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_est.so not built (needs /root/reference)")
+    lib = C.CDLL(path)
+    lib.ref_collect_stats.restype = C.c_longlong
+    lib.ref_collect_stats.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(11)
+    n, m, num_nn, k_star = 5000, 4, 6, 256
+    pq = rng.integers(0, 40, (n, m)).astype(np.uint8)         # few codes: well filled cells
+    nn = rng.integers(0, n, (n, num_nn)).astype(np.uint32)
+    nn[rng.random((n, num_nn)) < 0.05] = 0xFFFFFFFF            # unknown neighbours
+    for j in (0, 3, 5):
+        ref = np.empty((m, k_star, k_star), dtype=np.float64)
+        known = lib.ref_collect_stats(n, m, k_star, num_nn, pq.ctypes.data, nn.ctypes.data,
+                                      ref.ctypes.data, j)
+        got, got_known = ref_semantics.joint_histograms(pq, nn, k_star, j)
+        assert known == got_known
+        assert np.array_equal(ref.view(np.uint64), got.view(np.uint64))

@@ -336,11 +336,11 @@ def run_ours(args):
         os.environ["PQH_TC_DEBUG"] = "1"
         knn.init([local])
         vals = []
-        for _ in range(3):
+        for _ in range(2):      # (every row then goes to the exact kernel: ~15 s per run at 1M)
             device_step()
             torch.cuda.synchronize()
             vals.append(knn.last_stats()["ms_gemm"])
-        mma_only_ms = min(vals[1:])
+        mma_only_ms = vals[1]
         del os.environ["PQH_TC_DEBUG"]
         knn.init([local])
 
